@@ -1,0 +1,264 @@
+"""b2rsa - host-side binding of libb2rsa.so (hand-written sm_100a kernels behind a C ABI).
+
+This package is plumbing: it loads the in-tree shared library with ctypes and exposes the
+entry points of include/b2rsa.h on numpy arrays (host buffers) and raw device pointers
+(e.g. ``torch.Tensor.data_ptr()``).  There is no CPU fallback: if the library is missing
+or no sm_100 device is present, construction raises.
+
+Element format everywhere: halo2curves bn256 memory format - ``uint64[..., 4]``
+little-endian limbs in Montgomery form; G1Affine = ``uint64[..., 8]`` (x, y).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "..", "lib", "libb2rsa.so")
+
+OK = 0
+ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_LAYOUT, ERR_SYNTH = -1, -2, -3, -4, -5, -6
+
+
+class B2RError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb2rsa error {code}: {msg}")
+        self.code = code
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} not built: run `make -C halo2-rsa_b200` (or __graft_entry__.build()); "
+            "b2rsa has no CPU fallback")
+    lib = C.CDLL(os.path.abspath(path))
+    vp, u32, u64, i32, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_size_t
+    sigs = {
+        "b2r_ctx_create": [i32, C.POINTER(vp)],
+        "b2r_ctx_destroy": [vp],
+        "b2r_ctx_set_stream": [vp, vp],
+        "b2r_ctx_sync": [vp],
+        "b2r_dev_alloc": [vp, sz, C.POINTER(vp)],
+        "b2r_dev_free": [vp, vp],
+        "b2r_h2d": [vp, vp, vp, sz],
+        "b2r_d2h": [vp, vp, vp, sz],
+        "b2r_ntt_fr": [vp, vp, vp, u32],
+        "b2r_ntt_fr_dev": [vp, vp, vp, u32],
+        "b2r_ntt_fr_batch_dev": [vp, vp, sz, vp, u32],
+        "b2r_intt_fr": [vp, vp, u32],
+        "b2r_intt_fr_batch_dev": [vp, vp, sz, u32],
+        "b2r_coset_ntt_fr": [vp, vp, u32, u32, vp],
+        "b2r_coset_ntt_fr_batch_dev": [vp, vp, sz, u32, u32, vp],
+        "b2r_coset_intt_fr": [vp, vp, u32],
+        "b2r_coset_intt_fr_batch_dev": [vp, vp, sz, u32],
+        "b2r_bases_register": [vp, vp, sz, C.POINTER(vp)],
+        "b2r_bases_free": [vp, vp],
+        "b2r_msm_g1": [vp, vp, vp, sz, vp],
+        "b2r_msm_g1_batch": [vp, vp, vp, sz, sz, vp],
+        "b2r_msm_g1_batch_dev": [vp, vp, vp, sz, sz, vp],
+        "b2r_rsa_program_build": [vp, u32, vp, sz, u32, C.POINTER(vp)],
+        "b2r_prog_free": [vp, vp],
+        "b2r_prog_info": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
+        "b2r_rsa_witness_batch": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
+        "b2r_rsa_witness_batch_dev": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI symbol is missing: loud by design
+        fn.argtypes = args
+        fn.restype = i32
+    lib.b2r_last_error.argtypes = [vp]
+    lib.b2r_last_error.restype = C.c_char_p
+    lib.b2r_version.argtypes = []
+    lib.b2r_version.restype = C.c_char_p
+    lib.b2r_launch_count.argtypes = [vp]
+    lib.b2r_launch_count.restype = u64
+    return lib
+
+
+def _host_ptr(a: np.ndarray) -> C.c_void_p:
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+def _fr_array(a, shape_tail=4) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    assert a.shape[-1] == shape_tail, a.shape
+    return a
+
+
+class Context:
+    """One device, one stream (mirrors b2r_ctx)."""
+
+    def __init__(self, device: int = 0, lib: C.CDLL | None = None):
+        self.lib = lib or load_library()
+        h = C.c_void_p()
+        rc = self.lib.b2r_ctx_create(device, C.byref(h))
+        if rc != OK:
+            raise B2RError(rc, self.lib.b2r_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    # -- plumbing
+    def _ck(self, rc: int):
+        if rc != OK:
+            raise B2RError(rc, self.lib.b2r_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2r_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(self.lib.b2r_ctx_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        self._ck(self.lib.b2r_ctx_sync(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.b2r_launch_count(self.h))
+
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.lib.b2r_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, dptr: int):
+        self._ck(self.lib.b2r_dev_free(self.h, C.c_void_p(dptr)))
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        self._ck(self.lib.b2r_h2d(self.h, C.c_void_p(dptr), _host_ptr(arr), arr.nbytes))
+
+    def d2h(self, arr: np.ndarray, dptr: int):
+        self._ck(self.lib.b2r_d2h(self.h, _host_ptr(arr), C.c_void_p(dptr), arr.nbytes))
+
+    # -- NTT (best_fft and the EvaluationDomain wrappers)
+    def ntt(self, a: np.ndarray, omega: np.ndarray, log_n: int) -> np.ndarray:
+        """best_fft(a, omega, log_n): returns the transformed copy (natural order)."""
+        a = _fr_array(a).copy()
+        assert a.shape == (1 << log_n, 4)
+        omega = _fr_array(omega.reshape(4))
+        self._ck(self.lib.b2r_ntt_fr(self.h, _host_ptr(a), _host_ptr(omega), log_n))
+        return a
+
+    def intt(self, a: np.ndarray, k: int) -> np.ndarray:
+        a = _fr_array(a).copy()
+        assert a.shape == (1 << k, 4)
+        self._ck(self.lib.b2r_intt_fr(self.h, _host_ptr(a), k))
+        return a
+
+    def coset_ntt(self, coeffs: np.ndarray, k: int, ext_k: int) -> np.ndarray:
+        coeffs = _fr_array(coeffs)
+        assert coeffs.shape == (1 << k, 4)
+        out = np.empty((1 << ext_k, 4), dtype=np.uint64)
+        self._ck(self.lib.b2r_coset_ntt_fr(self.h, _host_ptr(coeffs), k, ext_k, _host_ptr(out)))
+        return out
+
+    def coset_intt(self, a: np.ndarray, ext_k: int) -> np.ndarray:
+        a = _fr_array(a).copy()
+        assert a.shape == (1 << ext_k, 4)
+        self._ck(self.lib.b2r_coset_intt_fr(self.h, _host_ptr(a), ext_k))
+        return a
+
+    def ntt_batch_dev(self, dptr: int, batch: int, omega: np.ndarray, log_n: int):
+        omega = _fr_array(omega.reshape(4))
+        self._ck(self.lib.b2r_ntt_fr_batch_dev(self.h, C.c_void_p(dptr), batch, _host_ptr(omega), log_n))
+
+    def intt_batch_dev(self, dptr: int, batch: int, k: int):
+        self._ck(self.lib.b2r_intt_fr_batch_dev(self.h, C.c_void_p(dptr), batch, k))
+
+    def coset_ntt_batch_dev(self, src: int, batch: int, k: int, ext_k: int, dst: int):
+        self._ck(self.lib.b2r_coset_ntt_fr_batch_dev(self.h, C.c_void_p(src), batch, k, ext_k, C.c_void_p(dst)))
+
+    def coset_intt_batch_dev(self, dptr: int, batch: int, ext_k: int):
+        self._ck(self.lib.b2r_coset_intt_fr_batch_dev(self.h, C.c_void_p(dptr), batch, ext_k))
+
+    # -- MSM (best_multiexp through ParamsKZG::commit / commit_lagrange)
+    def bases_register(self, bases: np.ndarray) -> "Bases":
+        bases = _fr_array(bases, 8)
+        h = C.c_void_p()
+        self._ck(self.lib.b2r_bases_register(self.h, _host_ptr(bases), bases.shape[0], C.byref(h)))
+        return Bases(self, h, bases.shape[0])
+
+    def msm(self, bases: "Bases", scalars: np.ndarray) -> np.ndarray:
+        """best_multiexp(scalars, bases[:len(scalars)]) -> uint64[12] Jacobian (z=1 or 0)."""
+        scalars = _fr_array(scalars)
+        out = np.zeros(12, dtype=np.uint64)
+        self._ck(self.lib.b2r_msm_g1(self.h, bases.h, _host_ptr(scalars), scalars.shape[0], _host_ptr(out)))
+        return out
+
+    def msm_batch(self, bases: "Bases", scalars: np.ndarray) -> np.ndarray:
+        """scalars uint64[m, n, 4] -> uint64[m, 8] affine commitments."""
+        scalars = _fr_array(scalars)
+        m, n = scalars.shape[0], scalars.shape[1]
+        out = np.zeros((m, 8), dtype=np.uint64)
+        self._ck(self.lib.b2r_msm_g1_batch(self.h, bases.h, _host_ptr(scalars), m, n, _host_ptr(out)))
+        return out
+
+    def msm_batch_dev(self, bases: "Bases", scalars_dptr: int, m: int, n: int, out_dptr: int):
+        self._ck(self.lib.b2r_msm_g1_batch_dev(self.h, bases.h, C.c_void_p(scalars_dptr), m, n, C.c_void_p(out_dptr)))
+
+    # -- RSA witness (Circuit::synthesize of the pkcs1v15 circuit)
+    def rsa_program(self, bits_len: int, k: int, e: int = 65537) -> "RsaProgram":
+        e_le = np.frombuffer(e.to_bytes((e.bit_length() + 7) // 8, "little"), dtype=np.uint8).copy()
+        h = C.c_void_p()
+        self._ck(self.lib.b2r_rsa_program_build(self.h, bits_len, _host_ptr(e_le), e_le.size, k, C.byref(h)))
+        return RsaProgram(self, h, bits_len, k)
+
+
+class Bases:
+    def __init__(self, ctx: Context, h, n: int):
+        self.ctx, self.h, self.n = ctx, h, n
+
+    def free(self):
+        if self.h:
+            self.ctx._ck(self.ctx.lib.b2r_bases_free(self.ctx.h, self.h))
+            self.h = None
+
+
+class RsaProgram:
+    """Recorded layout of the reference's pkcs1v15 circuit (benches/bench.rs:132-225)."""
+
+    def __init__(self, ctx: Context, h, bits_len: int, k: int):
+        self.ctx, self.h, self.bits_len, self.k = ctx, h, bits_len, k
+        self.num_limbs = bits_len // 64
+
+    def info(self):
+        r, v, l = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.ctx._ck(self.ctx.lib.b2r_prog_info(self.h, C.byref(r), C.byref(v), C.byref(l)))
+        return {"rows_used": r.value, "num_values": v.value, "num_levels": l.value}
+
+    def witness_batch(self, n_limbs, sig_limbs, hash_limbs, blind_seed: int = 0):
+        """-> (advice uint64[batch, 5, 2^k, 4], is_valid uint8[batch])"""
+        n_limbs = np.ascontiguousarray(n_limbs, dtype=np.uint64)
+        sig_limbs = np.ascontiguousarray(sig_limbs, dtype=np.uint64)
+        hash_limbs = np.ascontiguousarray(hash_limbs, dtype=np.uint64)
+        batch = n_limbs.shape[0]
+        assert n_limbs.shape == (batch, self.num_limbs) and sig_limbs.shape == (batch, self.num_limbs)
+        assert hash_limbs.shape == (batch, 4)
+        advice = np.empty((batch, 5, 1 << self.k, 4), dtype=np.uint64)
+        valid = np.zeros(batch, dtype=np.uint8)
+        self.ctx._ck(self.ctx.lib.b2r_rsa_witness_batch(
+            self.ctx.h, self.h, _host_ptr(n_limbs), _host_ptr(sig_limbs), _host_ptr(hash_limbs), batch,
+            blind_seed, _host_ptr(advice), _host_ptr(valid)))
+        return advice, valid
+
+    def witness_batch_dev(self, n_dptr: int, sig_dptr: int, hash_dptr: int, batch: int, blind_seed: int,
+                          advice_dptr: int, valid_dptr: int):
+        self.ctx._ck(self.ctx.lib.b2r_rsa_witness_batch_dev(
+            self.ctx.h, self.h, C.c_void_p(n_dptr), C.c_void_p(sig_dptr), C.c_void_p(hash_dptr), batch,
+            blind_seed, C.c_void_p(advice_dptr), C.c_void_p(valid_dptr)))
+
+    def free(self):
+        if self.h:
+            self.ctx._ck(self.ctx.lib.b2r_prog_free(self.ctx.h, self.h))
+            self.h = None

@@ -1,0 +1,146 @@
+// Context, error reporting and device-memory helpers of the C ABI (include/b2rsa.h).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "ctx.hpp"
+
+namespace b2r {
+
+int32_t fail(b2r_ctx* ctx, int32_t code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int32_t cuda_fail(b2r_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) {
+        ctx->err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    }
+    return e == cudaErrorMemoryAllocation ? B2R_ERR_NOMEM : B2R_ERR_CUDA;
+}
+
+int32_t scratch_get(b2r_ctx* ctx, int slot, size_t bytes, void** out) {
+    Scratch& s = ctx->scratch[slot];
+    if (s.cap < bytes) {
+        if (s.p) {
+            // stream-ordered: earlier kernels on the stream may still use the old block
+            B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            B2R_CUDA(ctx, cudaFree(s.p));
+            s.p = nullptr;
+            s.cap = 0;
+        }
+        size_t cap = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        B2R_CUDA(ctx, cudaMalloc(&s.p, cap));
+        s.cap = cap;
+    }
+    *out = s.p;
+    return 0;
+}
+
+}  // namespace b2r
+
+using namespace b2r;
+
+static thread_local std::string g_create_err;
+
+extern "C" {
+
+const char* b2r_version(void) { return "b2rsa 0.1 (sm_100a)"; }
+
+int32_t b2r_ctx_create(int32_t device, b2r_ctx** out) {
+    if (!out) return B2R_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_err = "no CUDA device: libb2rsa has no CPU fallback";
+        return B2R_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return B2R_ERR_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B2R_ERR_CUDA;
+    if (prop.major != 10) {
+        g_create_err = "device is not sm_100 (kernels are built for sm_100a only)";
+        return B2R_ERR_NO_DEVICE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return B2R_ERR_CUDA;
+    b2r_ctx* ctx = new (std::nothrow) b2r_ctx();
+    if (!ctx) return B2R_ERR_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return B2R_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+    *out = ctx;
+    return 0;
+}
+
+int32_t b2r_ctx_destroy(b2r_ctx* ctx) {
+    if (!ctx) return B2R_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->twiddles) cudaFree(kv.second);
+    for (auto& s : ctx->scratch)
+        if (s.p) cudaFree(s.p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int32_t b2r_ctx_set_stream(b2r_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return B2R_ERR_INVALID;
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        B2R_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return 0;
+}
+
+int32_t b2r_ctx_sync(b2r_ctx* ctx) {
+    if (!ctx) return B2R_ERR_INVALID;
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+const char* b2r_last_error(const b2r_ctx* ctx) {
+    if (!ctx) return g_create_err.c_str();
+    return ctx->err.c_str();
+}
+
+uint64_t b2r_launch_count(const b2r_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t b2r_dev_alloc(b2r_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return B2R_ERR_INVALID;
+    B2R_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+    return 0;
+}
+int32_t b2r_dev_free(b2r_ctx* ctx, void* dptr) {
+    if (!ctx) return B2R_ERR_INVALID;
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2R_CUDA(ctx, cudaFree(dptr));
+    return 0;
+}
+int32_t b2r_h2d(b2r_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (!ctx) return B2R_ERR_INVALID;
+    B2R_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int32_t b2r_d2h(b2r_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (!ctx) return B2R_ERR_INVALID;
+    B2R_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Internal context shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b2rsa.h"
+#include "field.cuh"
+
+namespace b2r {
+
+struct TwiddleKey {
+    uint32_t log_n;
+    uint64_t w[4];
+    bool operator<(const TwiddleKey& o) const {
+        if (log_n != o.log_n) return log_n < o.log_n;
+        for (int i = 0; i < 4; i++)
+            if (w[i] != o.w[i]) return w[i] < o.w[i];
+        return false;
+    }
+};
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace b2r
+
+struct b2r_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    uint64_t launches = 0;
+    // twiddle tables: omega^e, e < n/2, Montgomery form, device resident
+    std::map<b2r::TwiddleKey, b2r::fe_t*> twiddles;
+    // grow-only scratch arenas (ping-pong buffers, MSM work arrays, staging)
+    b2r::Scratch scratch[8];
+    void* pinned = nullptr;  // small pinned staging block
+    size_t pinned_cap = 0;
+};
+
+namespace b2r {
+
+int32_t fail(b2r_ctx* ctx, int32_t code, const std::string& msg);
+int32_t cuda_fail(b2r_ctx* ctx, cudaError_t e, const char* what);
+// returns device pointer of at least `bytes` from arena `slot` (contents undefined)
+int32_t scratch_get(b2r_ctx* ctx, int slot, size_t bytes, void** out);
+
+#define B2R_CUDA(ctx, call)                                          \
+    do {                                                             \
+        cudaError_t _e = (call);                                     \
+        if (_e != cudaSuccess) return b2r::cuda_fail(ctx, _e, #call); \
+    } while (0)
+
+#define B2R_TRY(expr)            \
+    do {                         \
+        int32_t _r = (expr);     \
+        if (_r != 0) return _r;  \
+    } while (0)
+
+#define B2R_LAUNCH_CHECK(ctx)                                                  \
+    do {                                                                       \
+        (ctx)->launches++;                                                     \
+        cudaError_t _e = cudaGetLastError();                                   \
+        if (_e != cudaSuccess) return b2r::cuda_fail(ctx, _e, "kernel launch"); \
+    } while (0)
+
+// scratch arena slots
+enum { SC_NTT_PING = 0, SC_NTT_PONG = 1, SC_MSM_A = 2, SC_MSM_B = 3, SC_MSM_C = 4, SC_STAGE = 5, SC_WIT = 6, SC_MISC = 7 };
+
+// ntt.cu
+int32_t ntt_get_twiddles(b2r_ctx* ctx, const fe_t& omega, uint32_t log_n, const fe_t** out);
+
+}  // namespace b2r

@@ -1,0 +1,153 @@
+// BN254 G1 (y^2 = x^3 + 3 over Fq) point arithmetic in extended Jacobian ("XYZZ")
+// coordinates: x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; identity has ZZ = 0.
+// Mixed addition costs 8M + 2S, full addition 12M + 2S (EFD madd-2008-s / add-2008-s /
+// dbl-2008-s-1 with a = 0).  All exceptional cases (identity operands, P + P, P - P) are
+// handled because resident base tables do contain repeated points (2^c * P_i == P_j).
+#pragma once
+#include "field.cuh"
+
+namespace b2r {
+
+struct affine_t {
+    fe_t x, y;  // identity = (0, 0), halo2curves convention
+};
+struct xyzz_t {
+    fe_t x, y, zz, zzz;
+};
+
+B2R_HD bool affine_is_identity(const affine_t& p) { return Fq::is_zero(p.x) && Fq::is_zero(p.y); }
+B2R_HD bool xyzz_is_identity(const xyzz_t& p) { return Fq::is_zero(p.zz); }
+B2R_HD xyzz_t xyzz_identity() {
+    xyzz_t r;
+    r.x = Fq::zero();
+    r.y = Fq::zero();
+    r.zz = Fq::zero();
+    r.zzz = Fq::zero();
+    return r;
+}
+B2R_HD xyzz_t xyzz_from_affine(const affine_t& p) {
+    if (affine_is_identity(p)) return xyzz_identity();
+    xyzz_t r;
+    r.x = p.x;
+    r.y = p.y;
+    r.zz = Fq::one();
+    r.zzz = Fq::one();
+    return r;
+}
+
+// 2 * (x, y) for an affine, non-identity point (mdbl-2008-s-1)
+B2R_HD xyzz_t xyzz_double_affine(const affine_t& p) {
+    fe_t U = Fq::dbl(p.y);
+    fe_t V = Fq::sqr(U);
+    fe_t W = Fq::mul(U, V);
+    fe_t S = Fq::mul(p.x, V);
+    fe_t xx = Fq::sqr(p.x);
+    fe_t M = Fq::add(Fq::dbl(xx), xx);
+    xyzz_t r;
+    r.x = Fq::sub(Fq::sqr(M), Fq::dbl(S));
+    r.y = Fq::sub(Fq::mul(M, Fq::sub(S, r.x)), Fq::mul(W, p.y));
+    r.zz = V;
+    r.zzz = W;
+    return r;  // y == 0 cannot happen on a prime-order curve
+}
+
+B2R_HD xyzz_t xyzz_double(const xyzz_t& p) {
+    if (xyzz_is_identity(p)) return p;
+    fe_t U = Fq::dbl(p.y);
+    fe_t V = Fq::sqr(U);
+    fe_t W = Fq::mul(U, V);
+    fe_t S = Fq::mul(p.x, V);
+    fe_t xx = Fq::sqr(p.x);
+    fe_t M = Fq::add(Fq::dbl(xx), xx);
+    xyzz_t r;
+    r.x = Fq::sub(Fq::sqr(M), Fq::dbl(S));
+    r.y = Fq::sub(Fq::mul(M, Fq::sub(S, r.x)), Fq::mul(W, p.y));
+    r.zz = Fq::mul(V, p.zz);
+    r.zzz = Fq::mul(W, p.zzz);
+    return r;
+}
+
+// acc += q (affine); `neg` adds -q
+B2R_HD void xyzz_madd(xyzz_t& acc, const affine_t& q, bool neg) {
+    if (affine_is_identity(q)) return;
+    fe_t qy = neg ? Fq::neg(q.y) : q.y;
+    if (xyzz_is_identity(acc)) {
+        acc.x = q.x;
+        acc.y = qy;
+        acc.zz = Fq::one();
+        acc.zzz = Fq::one();
+        return;
+    }
+    fe_t U2 = Fq::mul(q.x, acc.zz);
+    fe_t S2 = Fq::mul(qy, acc.zzz);
+    fe_t P = Fq::sub(U2, acc.x);
+    fe_t R = Fq::sub(S2, acc.y);
+    if (Fq::is_zero(P)) {
+        if (Fq::is_zero(R)) {
+            affine_t t;
+            t.x = q.x;
+            t.y = qy;
+            acc = xyzz_double_affine(t);
+        } else {
+            acc = xyzz_identity();
+        }
+        return;
+    }
+    fe_t PP = Fq::sqr(P);
+    fe_t PPP = Fq::mul(P, PP);
+    fe_t Q = Fq::mul(acc.x, PP);
+    fe_t X3 = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
+    fe_t Y3 = Fq::sub(Fq::mul(R, Fq::sub(Q, X3)), Fq::mul(acc.y, PPP));
+    acc.x = X3;
+    acc.y = Y3;
+    acc.zz = Fq::mul(acc.zz, PP);
+    acc.zzz = Fq::mul(acc.zzz, PPP);
+}
+
+// acc += q (XYZZ)
+B2R_HD void xyzz_add(xyzz_t& acc, const xyzz_t& q) {
+    if (xyzz_is_identity(q)) return;
+    if (xyzz_is_identity(acc)) {
+        acc = q;
+        return;
+    }
+    fe_t U1 = Fq::mul(acc.x, q.zz);
+    fe_t U2 = Fq::mul(q.x, acc.zz);
+    fe_t S1 = Fq::mul(acc.y, q.zzz);
+    fe_t S2 = Fq::mul(q.y, acc.zzz);
+    fe_t P = Fq::sub(U2, U1);
+    fe_t R = Fq::sub(S2, S1);
+    if (Fq::is_zero(P)) {
+        if (Fq::is_zero(R)) {
+            acc = xyzz_double(acc);
+        } else {
+            acc = xyzz_identity();
+        }
+        return;
+    }
+    fe_t PP = Fq::sqr(P);
+    fe_t PPP = Fq::mul(P, PP);
+    fe_t Q = Fq::mul(U1, PP);
+    fe_t X3 = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
+    fe_t Y3 = Fq::sub(Fq::mul(R, Fq::sub(Q, X3)), Fq::mul(S1, PPP));
+    acc.x = X3;
+    acc.y = Y3;
+    acc.zz = Fq::mul(Fq::mul(acc.zz, q.zz), PP);
+    acc.zzz = Fq::mul(Fq::mul(acc.zzz, q.zzz), PPP);
+}
+
+// normalise; identity -> (0, 0)
+B2R_HD affine_t xyzz_to_affine(const xyzz_t& p) {
+    affine_t r;
+    if (xyzz_is_identity(p)) {
+        r.x = Fq::zero();
+        r.y = Fq::zero();
+        return r;
+    }
+    fe_t t = Fq::inv(Fq::mul(p.zz, p.zzz));
+    r.x = Fq::mul(p.x, Fq::mul(t, p.zzz));  // X / ZZ
+    r.y = Fq::mul(p.y, Fq::mul(t, p.zz));   // Y / ZZZ
+    return r;
+}
+
+}  // namespace b2r

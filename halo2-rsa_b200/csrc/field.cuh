@@ -1,0 +1,350 @@
+// BN254 Fr / Fq arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form (R = 2^256).
+//
+// Memory format is halo2curves' bn256::{Fr,Fq}: 4 x u64 little-endian limbs in
+// Montgomery form == 8 x u32 little-endian limbs, so a Rust &[Fr] can be handed to the
+// kernels as a raw pointer.
+//
+// Montgomery multiplication is an interleaved (CIOS-style) product/reduction held in two
+// 64-bit-lane accumulators ("primary" P at word offset 0 and "secondary" S at word
+// offset 1, T = P + 2^32 * S).  Every 32x32->64 product is one mad.lo.cc/madc.hi.cc pair
+// that ptxas fuses into a single IMAD.WIDE.U32 with carry-in/out, so a full multiply is
+// ~130 wide MADs + ~50 carry/select instructions and no spills.
+//
+// The same source compiles for the host (plain C emulation of the row primitives): that
+// is how the carry logic is unit-tested in this GPU-less container
+// (tests/host/field_host_test.cpp).  The host build is test scaffolding for the device
+// algorithm, not a CPU fallback: no product path calls it.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2R_HD __host__ __device__ __forceinline__
+#define B2R_D __device__ __forceinline__
+#else
+#define B2R_HD inline
+#define B2R_D inline
+#endif
+
+namespace b2r {
+
+struct alignas(16) fe_t {
+    uint32_t l[8];
+};
+
+// ---- field parameter packs --------------------------------------------------------------
+struct FrP {
+    // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+    B2R_HD static constexpr uint32_t MOD(int i) {
+        constexpr uint32_t v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                        0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    static constexpr uint32_t N0INV = 0xefffffffu;  // -r^-1 mod 2^32
+    // R mod r
+    B2R_HD static constexpr uint32_t ONE(int i) {
+        constexpr uint32_t v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                                        0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    // R^2 mod r
+    B2R_HD static constexpr uint32_t R2(int i) {
+        constexpr uint32_t v[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                                       0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return v[i];
+    }
+};
+
+struct FqP {
+    // q = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+    B2R_HD static constexpr uint32_t MOD(int i) {
+        constexpr uint32_t v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                                        0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    static constexpr uint32_t N0INV = 0xe4866389u;  // -q^-1 mod 2^32
+    // R mod q
+    B2R_HD static constexpr uint32_t ONE(int i) {
+        constexpr uint32_t v[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                                        0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    // R^2 mod q
+    B2R_HD static constexpr uint32_t R2(int i) {
+        constexpr uint32_t v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                                       0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return v[i];
+    }
+};
+
+// ---- row primitives ----------------------------------------------------------------------
+// A "row" is four 64-bit lanes: lane l covers words (2l, 2l+1).  `a` is indexed with
+// stride 2 (a[0], a[2], a[4], a[6]); pass &x[0] for the even limbs, &x[1] for the odd.
+
+// X[0..7] = lanes a[2l] * w
+B2R_HD void row_mul(uint32_t* X, const uint32_t* a, uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    asm("mul.lo.u32 %0, %8, %12; mul.hi.u32 %1, %8, %12;"
+        "mul.lo.u32 %2, %9, %12; mul.hi.u32 %3, %9, %12;"
+        "mul.lo.u32 %4, %10, %12; mul.hi.u32 %5, %10, %12;"
+        "mul.lo.u32 %6, %11, %12; mul.hi.u32 %7, %11, %12;"
+        : "=&r"(X[0]), "=&r"(X[1]), "=&r"(X[2]), "=&r"(X[3]), "=&r"(X[4]), "=&r"(X[5]),
+          "=&r"(X[6]), "=&r"(X[7])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(w));
+#else
+    for (int l = 0; l < 4; l++) {
+        uint64_t p = (uint64_t)a[2 * l] * w;
+        X[2 * l] = (uint32_t)p;
+        X[2 * l + 1] = (uint32_t)(p >> 32);
+    }
+#endif
+}
+
+// X[0..7] += lanes a[2l] * w ; returns carry out of word 7 (0 or 1)
+B2R_HD uint32_t row_mad(uint32_t* X, const uint32_t* a, uint32_t w) {
+    uint32_t c;
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u32 %0, %9, %13, %0; madc.hi.cc.u32 %1, %9, %13, %1;"
+        "madc.lo.cc.u32 %2, %10, %13, %2; madc.hi.cc.u32 %3, %10, %13, %3;"
+        "madc.lo.cc.u32 %4, %11, %13, %4; madc.hi.cc.u32 %5, %11, %13, %5;"
+        "madc.lo.cc.u32 %6, %12, %13, %6; madc.hi.cc.u32 %7, %12, %13, %7;"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]),
+          "+r"(X[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(w));
+#else
+    uint64_t cy = 0;
+    for (int l = 0; l < 4; l++) {
+        uint64_t x = (uint64_t)X[2 * l] | ((uint64_t)X[2 * l + 1] << 32);
+        unsigned __int128 t = (unsigned __int128)a[2 * l] * w + x + cy;
+        X[2 * l] = (uint32_t)t;
+        X[2 * l + 1] = (uint32_t)(t >> 32);
+        cy = (uint64_t)(t >> 64);
+    }
+    c = (uint32_t)cy;
+#endif
+    return c;
+}
+
+// same, carry out of word 7 is known to be zero by a value bound (not materialised)
+B2R_HD void row_mad_nc(uint32_t* X, const uint32_t* a, uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u32 %0, %8, %12, %0; madc.hi.cc.u32 %1, %8, %12, %1;"
+        "madc.lo.cc.u32 %2, %9, %12, %2; madc.hi.cc.u32 %3, %9, %12, %3;"
+        "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5;"
+        "madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]),
+          "+r"(X[7])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(w));
+#else
+    (void)row_mad(X, a, w);
+#endif
+}
+
+// The shift step.  In:  P[0..8] (P[0] == 0 mod 2^32 already consumed), S[0..7].
+// Computes  S[0] += P[1]  (carry c), then  Q = (P >> 64) + lanes a[2l]*w + c  where
+// (P >> 64) = words P[2..8] followed by a zero word.  Q is written over P[2..9].
+B2R_HD void row_shift_mad(uint32_t* P /*10 words*/, uint32_t* S0, const uint32_t* a, uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %8, %8, %9;"
+        "madc.lo.cc.u32 %0, %10, %14, %0; madc.hi.cc.u32 %1, %10, %14, %1;"
+        "madc.lo.cc.u32 %2, %11, %14, %2; madc.hi.cc.u32 %3, %11, %14, %3;"
+        "madc.lo.cc.u32 %4, %12, %14, %4; madc.hi.cc.u32 %5, %12, %14, %5;"
+        "madc.lo.cc.u32 %6, %13, %14, %6; madc.hi.u32 %7, %13, %14, 0;"
+        : "+r"(P[2]), "+r"(P[3]), "+r"(P[4]), "+r"(P[5]), "+r"(P[6]), "+r"(P[7]), "+r"(P[8]),
+          "=&r"(P[9]), "+r"(*S0)
+        : "r"(P[1]), "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(w));
+#else
+    uint64_t s = (uint64_t)*S0 + P[1];
+    *S0 = (uint32_t)s;
+    uint64_t cy = s >> 32;
+    P[9] = 0;
+    for (int l = 0; l < 4; l++) {
+        uint64_t x = (uint64_t)P[2 + 2 * l] | ((uint64_t)P[3 + 2 * l] << 32);
+        unsigned __int128 t = (unsigned __int128)a[2 * l] * w + x + cy;
+        P[2 + 2 * l] = (uint32_t)t;
+        P[3 + 2 * l] = (uint32_t)(t >> 32);
+        cy = (uint64_t)(t >> 64);
+    }
+#endif
+}
+
+// 8-word add / sub with carry chains
+B2R_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t c;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19;"
+        "addc.cc.u32 %3, %12, %20; addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22;"
+        "addc.cc.u32 %6, %15, %23; addc.cc.u32 %7, %16, %24; addc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]),
+          "=&r"(r[6]), "=&r"(r[7]), "=&r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]),
+          "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]),
+          "r"(b[6]), "r"(b[7]));
+#else
+    uint64_t cy = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t t = (uint64_t)a[i] + b[i] + cy;
+        r[i] = (uint32_t)t;
+        cy = t >> 32;
+    }
+    c = (uint32_t)cy;
+#endif
+    return c;
+}
+
+// r = a - b, returns borrow (1 if a < b)
+B2R_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t bw;
+#if defined(__CUDA_ARCH__)
+    asm("sub.cc.u32 %0, %9, %17; subc.cc.u32 %1, %10, %18; subc.cc.u32 %2, %11, %19;"
+        "subc.cc.u32 %3, %12, %20; subc.cc.u32 %4, %13, %21; subc.cc.u32 %5, %14, %22;"
+        "subc.cc.u32 %6, %15, %23; subc.cc.u32 %7, %16, %24; subc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]),
+          "=&r"(r[6]), "=&r"(r[7]), "=&r"(bw)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]),
+          "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]),
+          "r"(b[6]), "r"(b[7]));
+    bw &= 1u;
+#else
+    int64_t br = 0;
+    for (int i = 0; i < 8; i++) {
+        int64_t t = (int64_t)a[i] - b[i] - br;
+        r[i] = (uint32_t)t;
+        br = (t < 0) ? 1 : 0;
+    }
+    bw = (uint32_t)br;
+#endif
+    return bw;
+}
+
+// ---- field ops -----------------------------------------------------------------------------
+template <class P>
+struct Field {
+    B2R_HD static fe_t zero() {
+        fe_t r;
+        for (int i = 0; i < 8; i++) r.l[i] = 0;
+        return r;
+    }
+    B2R_HD static fe_t one() {
+        fe_t r;
+        for (int i = 0; i < 8; i++) r.l[i] = P::ONE(i);
+        return r;
+    }
+    B2R_HD static fe_t r2() {
+        fe_t r;
+        for (int i = 0; i < 8; i++) r.l[i] = P::R2(i);
+        return r;
+    }
+    B2R_HD static bool is_zero(const fe_t& a) {
+        uint32_t o = 0;
+        for (int i = 0; i < 8; i++) o |= a.l[i];
+        return o == 0;
+    }
+    B2R_HD static bool eq(const fe_t& a, const fe_t& b) {
+        uint32_t o = 0;
+        for (int i = 0; i < 8; i++) o |= a.l[i] ^ b.l[i];
+        return o == 0;
+    }
+    // r = (x >= p) ? x - p : x      for x < 2p
+    B2R_HD static void final_sub(uint32_t* x) {
+        uint32_t m[8], t[8];
+        for (int i = 0; i < 8; i++) m[i] = P::MOD(i);
+        uint32_t bw = sub8(t, x, m);
+        for (int i = 0; i < 8; i++) x[i] = bw ? x[i] : t[i];
+    }
+    B2R_HD static fe_t add(const fe_t& a, const fe_t& b) {
+        fe_t r;
+        add8(r.l, a.l, b.l);  // < 2p < 2^255: no carry out
+        final_sub(r.l);
+        return r;
+    }
+    B2R_HD static fe_t dbl(const fe_t& a) { return add(a, a); }
+    B2R_HD static fe_t sub(const fe_t& a, const fe_t& b) {
+        fe_t r;
+        uint32_t m[8], t[8];
+        for (int i = 0; i < 8; i++) m[i] = P::MOD(i);
+        uint32_t bw = sub8(r.l, a.l, b.l);
+        add8(t, r.l, m);
+        for (int i = 0; i < 8; i++) r.l[i] = bw ? t[i] : r.l[i];
+        return r;
+    }
+    B2R_HD static fe_t neg(const fe_t& a) {
+        fe_t r;
+        uint32_t m[8];
+        for (int i = 0; i < 8; i++) m[i] = P::MOD(i);
+        sub8(r.l, m, a.l);
+        bool z = is_zero(a);
+        for (int i = 0; i < 8; i++) r.l[i] = z ? 0u : r.l[i];
+        return r;
+    }
+
+    // Montgomery product a*b*R^-1 mod p, inputs and output fully reduced (< p).
+    // Invariant per iteration (T = Pw + 2^32 * Sw): T < a + p < 2^255 at iteration start,
+    // so the S chains never carry out of 8 words and Pw needs one carry word (<= 2).
+    B2R_HD static fe_t mul(const fe_t& a, const fe_t& b) {
+        uint32_t m[8];
+        for (int i = 0; i < 8; i++) m[i] = P::MOD(i);
+        uint32_t Pw[10], Sw[10];
+        // i = 0
+        row_mul(Pw, &a.l[0], b.l[0]);
+        row_mul(Sw, &a.l[1], b.l[0]);
+        uint32_t mi = Pw[0] * P::N0INV;
+        Pw[8] = row_mad(Pw, &m[0], mi);
+        row_mad_nc(Sw, &m[1], mi);
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            // T /= 2^32 and T += a * b[i]:   newP = S + P[1],  newS = (P >> 64) + odd(a)*b[i] + carry
+            row_shift_mad(Pw, &Sw[0], &a.l[1], b.l[i]);
+            uint32_t nP[10], nS[10];
+            for (int k = 0; k < 8; k++) nS[k] = Pw[k + 2];
+            for (int k = 0; k < 8; k++) nP[k] = Sw[k];
+            nP[8] = row_mad(nP, &a.l[0], b.l[i]);
+            mi = nP[0] * P::N0INV;
+            nP[8] += row_mad(nP, &m[0], mi);
+            row_mad_nc(nS, &m[1], mi);
+            for (int k = 0; k < 9; k++) Pw[k] = nP[k];
+            for (int k = 0; k < 8; k++) Sw[k] = nS[k];
+        }
+        // final shift: result = S + P[1] + 2^32 * (P >> 64)  ==  S + (P >> 32)
+        fe_t r;
+        add8(r.l, Sw, &Pw[1]);
+        final_sub(r.l);
+        return r;
+    }
+    B2R_HD static fe_t sqr(const fe_t& a) { return mul(a, a); }
+
+    B2R_HD static fe_t to_mont(const fe_t& a) { return mul(a, r2()); }
+    B2R_HD static fe_t from_mont(const fe_t& a) {
+        fe_t o = zero();
+        o.l[0] = 1;
+        return mul(a, o);
+    }
+
+    // a^e, e given as 8 little-endian words (not secret: variable time)
+    B2R_HD static fe_t pow(const fe_t& a, const uint32_t* e) {
+        fe_t acc = one();
+        bool started = false;
+        for (int w = 7; w >= 0; w--) {
+            for (int bit = 31; bit >= 0; bit--) {
+                if (started) acc = sqr(acc);
+                if ((e[w] >> bit) & 1u) {
+                    acc = started ? mul(acc, a) : a;
+                    started = true;
+                }
+            }
+        }
+        return acc;
+    }
+    // a^-1 = a^(p-2) (Fermat); inv(0) = 0
+    B2R_HD static fe_t inv(const fe_t& a) {
+        uint32_t e[8];
+        for (int i = 0; i < 8; i++) e[i] = P::MOD(i);
+        e[0] -= 2u;  // both moduli end in ...01 / ...47: no borrow
+        return pow(a, e);
+    }
+};
+
+using Fr = Field<FrP>;
+using Fq = Field<FqP>;
+
+}  // namespace b2r

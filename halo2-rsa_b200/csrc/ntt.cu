@@ -1,0 +1,412 @@
+// Radix-2 Stockham (autosort) NTT over BN254 Fr for sm_100a.
+//
+// Replaces halo2_proofs::arithmetic::best_fft and the EvaluationDomain wrappers around it
+// (lagrange_to_coeff / coeff_to_extended / extended_to_coeff); call sites in the reference:
+// benches/bench.rs:236-237 (keygen) and :321-329 (create_proof).
+//
+// Structure: log_n radix-2 Stockham stages are grouped into passes of S <= 9 stages.  A
+// Stockham stage with length l and stride s (l*s = n) maps
+//     a = x[q + s*p], b = x[q + s*(p + l/2)]  ->  y[q + s*2p] = a + b,  y[q + s*(2p+1)] = (a - b) * w_l^p.
+// S consecutive stages only mix the R = 2^S elements x[c + (n/R)*r], r < R, of one "column"
+// c = q + s*p', so one CTA stages C adjacent columns (C*32 B contiguous per row, 128-bit
+// loads) in shared memory, runs the S stages there and writes every element once:
+// out index q + s*(R*p' + bitrev_S(r)).  No bit-reversal pass, natural order in and out.
+// HBM traffic = 2 * n * 32 B per pass (+ the twiddle table, L2 resident for n <= 2^20).
+// Scaling (1/n) and the coset ZETA-power twists are fused into the first load / last store.
+#include <cuda_runtime.h>
+
+#include "ctx.hpp"
+
+namespace b2r {
+
+// ---- twiddle table: tw[e] = omega^e, e < n/2 ------------------------------------------
+__global__ void k_twiddles(fe_t* tw, fe_t omega, uint32_t count) {
+    const uint32_t CH = 64;
+    uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t e0 = chunk * CH;
+    if (e0 >= count) return;
+    uint32_t ew[8] = {e0, 0, 0, 0, 0, 0, 0, 0};
+    fe_t cur = Fr::pow(omega, ew);
+    for (uint32_t j = 0; j < CH && e0 + j < count; j++) {
+        tw[e0 + j] = cur;
+        cur = Fr::mul(cur, omega);
+    }
+}
+
+struct NttPassArgs {
+    const fe_t* x;
+    fe_t* y;
+    const fe_t* tw;       // omega^e, e < n/2
+    uint64_t in_stride;   // elements between consecutive vectors of the batch (input)
+    uint64_t out_stride;  // same for output
+    uint32_t in_len;      // valid input elements per vector (rest read as zero)
+    uint32_t log_n;
+    uint32_t log_s;  // stride s = 2^log_s = product of the radices of earlier passes
+    uint32_t log_c;  // columns per CTA
+    uint32_t pre;    // multiply input element i by pre3[i % 3]
+    uint32_t post;   // multiply output element i by post3[i % 3]
+    fe_t pre3[3];
+    fe_t post3[3];
+};
+
+__device__ __forceinline__ fe_t ld_fe(const fe_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fe_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ fe_t ld_fe_nc(const fe_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    fe_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fe(fe_t* p, const fe_t& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
+    constexpr uint32_t R = 1u << S;
+    extern __shared__ uint4 smem_raw[];
+    fe_t* sm = reinterpret_cast<fe_t*>(smem_raw);
+    const uint32_t T = blockDim.x, tid = threadIdx.x;
+    const uint32_t log_c = A.log_c, C = 1u << log_c, cmask = C - 1;
+    const uint32_t log_cols = A.log_n - S;  // columns = n / R
+    const uint32_t c0 = blockIdx.x << log_c;
+    const fe_t* x = A.x + (uint64_t)blockIdx.y * A.in_stride;
+    fe_t* y = A.y + (uint64_t)blockIdx.y * A.out_stride;
+    const uint32_t smask = (1u << A.log_s) - 1;
+
+    // ---- load R rows x C columns (row r of column c lives at c + (n/R)*r)
+    for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
+        uint32_t r = idx >> log_c, c = idx & cmask;
+        uint32_t gi = c0 + c + (r << log_cols);
+        fe_t v;
+        if (gi < A.in_len) {
+            v = ld_fe(x + gi);
+            if (A.pre) {
+                uint32_t m3 = gi % 3u;
+                if (m3) v = Fr::mul(v, A.pre3[m3]);
+            }
+        } else {
+            v = Fr::zero();
+        }
+        st_fe(sm + idx, v);
+    }
+    __syncthreads();
+
+    // ---- S radix-2 stages in shared memory (decimation in frequency, in place)
+#pragma unroll 1
+    for (uint32_t i = 0; i < S; i++) {
+        const uint32_t log_half = S - 1 - i, half = 1u << log_half;
+        for (uint32_t b = tid; b < ((R / 2) << log_c); b += T) {
+            uint32_t c = b & cmask, bf = b >> log_c;
+            uint32_t blk = bf >> log_half, rp = bf & (half - 1);
+            uint32_t i0 = (((blk << (log_half + 1)) + rp) << log_c) + c;
+            uint32_t i1 = i0 + (half << log_c);
+            uint32_t pp = (c0 + c) >> A.log_s;  // p'
+            // exponent of omega_n: s*2^i*(p' + (l/R)*r')
+            uint32_t e = ((pp << A.log_s) << i) + ((rp << log_cols) << i);
+            fe_t a = ld_fe(sm + i0), bb = ld_fe(sm + i1);
+            fe_t u = Fr::add(a, bb);
+            fe_t d = Fr::sub(a, bb);
+            if (e) d = Fr::mul(d, ld_fe_nc(A.tw + e));
+            st_fe(sm + i0, u);
+            st_fe(sm + i1, d);
+        }
+        __syncthreads();
+    }
+
+    // ---- store: local row r holds output digit t = bitrev_S(r)
+    if (A.log_s == 0) {
+        // first pass: out index = R*col + t, make t the fastest index for contiguous stores
+        for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
+            uint32_t t = idx & (R - 1), c = idx >> S;
+            uint32_t r = __brev(t) >> (32 - S);
+            fe_t v = ld_fe(sm + (r << log_c) + c);
+            uint32_t oi = ((c0 + c) << S) + t;
+            if (A.post) v = Fr::mul(v, A.post3[oi % 3u]);
+            st_fe(y + oi, v);
+        }
+    } else {
+        for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
+            uint32_t r = idx >> log_c, c = idx & cmask;
+            uint32_t t = __brev(r) >> (32 - S);
+            uint32_t col = c0 + c, q = col & smask, pp = col >> A.log_s;
+            uint32_t oi = q + (pp << (A.log_s + S)) + (t << A.log_s);
+            fe_t v = ld_fe(sm + idx);
+            if (A.post) v = Fr::mul(v, A.post3[oi % 3u]);
+            st_fe(y + oi, v);
+        }
+    }
+}
+
+typedef void (*ntt_kernel_t)(const NttPassArgs);
+static ntt_kernel_t pass_kernel(int S) {
+    switch (S) {
+        case 1: return k_ntt_pass<1>;
+        case 2: return k_ntt_pass<2>;
+        case 3: return k_ntt_pass<3>;
+        case 4: return k_ntt_pass<4>;
+        case 5: return k_ntt_pass<5>;
+        case 6: return k_ntt_pass<6>;
+        case 7: return k_ntt_pass<7>;
+        case 8: return k_ntt_pass<8>;
+        case 9: return k_ntt_pass<9>;
+        default: return nullptr;
+    }
+}
+
+int32_t ntt_get_twiddles(b2r_ctx* ctx, const fe_t& omega, uint32_t log_n, const fe_t** out) {
+    TwiddleKey key;
+    key.log_n = log_n;
+    for (int i = 0; i < 4; i++) key.w[i] = (uint64_t)omega.l[2 * i] | ((uint64_t)omega.l[2 * i + 1] << 32);
+    auto it = ctx->twiddles.find(key);
+    if (it != ctx->twiddles.end()) {
+        *out = it->second;
+        return 0;
+    }
+    uint32_t count = log_n == 0 ? 1 : (1u << (log_n - 1));
+    fe_t* d = nullptr;
+    B2R_CUDA(ctx, cudaMalloc(&d, (size_t)count * sizeof(fe_t)));
+    uint32_t chunks = (count + 63) / 64;
+    k_twiddles<<<(chunks + 127) / 128, 128, 0, ctx->stream>>>(d, omega, count);
+    B2R_LAUNCH_CHECK(ctx);
+    ctx->twiddles[key] = d;
+    *out = d;
+    return 0;
+}
+
+// domain constants (host): omega_k = ROOT_OF_UNITY^(2^(28-k))
+static fe_t root_of_unity() {
+    // 0x03ddb9f5166d18b798865ea93dd31f743215cf6dd39329c8d34f1ed960c37c9c, canonical
+    fe_t c;
+    const uint32_t w[8] = {0x60c37c9cu, 0xd34f1ed9u, 0xd39329c8u, 0x3215cf6du,
+                           0x3dd31f74u, 0x98865ea9u, 0x166d18b7u, 0x03ddb9f5u};
+    for (int i = 0; i < 8; i++) c.l[i] = w[i];
+    return Fr::to_mont(c);
+}
+fe_t fr_omega(uint32_t k) {
+    fe_t w = root_of_unity();
+    for (uint32_t i = k; i < 28; i++) w = Fr::sqr(w);
+    return w;
+}
+fe_t fr_zeta() {
+    // 0x30644e72e131a029048b6e193fd84104cc37a73fec2bc5e9b8ca0b2d36636f23, canonical
+    fe_t c;
+    const uint32_t w[8] = {0x36636f23u, 0xb8ca0b2du, 0xec2bc5e9u, 0xcc37a73fu,
+                           0x3fd84104u, 0x048b6e19u, 0xe131a029u, 0x30644e72u};
+    for (int i = 0; i < 8; i++) c.l[i] = w[i];
+    return Fr::to_mont(c);
+}
+fe_t fr_from_u64(uint64_t v) {
+    fe_t c = Fr::zero();
+    c.l[0] = (uint32_t)v;
+    c.l[1] = (uint32_t)(v >> 32);
+    return Fr::to_mont(c);
+}
+
+enum NttMode { MODE_PLAIN = 0, MODE_INV = 1, MODE_COSET_FWD = 2, MODE_COSET_INV = 3 };
+
+// Runs the passes.  in: `batch` vectors of in_len valid elements (stride in_stride);
+// out: 2^log_n elements each (stride out_stride).  `in` may equal `out` (in place).
+static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_t in_len, fe_t* out,
+                       uint64_t out_stride, size_t batch, const fe_t& omega, uint32_t log_n, int mode) {
+    if (log_n > 27) return fail(ctx, B2R_ERR_INVALID, "ntt: log_n > 27");
+    if (batch == 0) return 0;
+    if (batch > 65535) return fail(ctx, B2R_ERR_INVALID, "ntt: batch > 65535");
+    const uint64_t n = 1ull << log_n;
+    if (log_n == 0) {
+        if (in != out) B2R_CUDA(ctx, cudaMemcpy2DAsync(out, out_stride * 32, in, in_stride * 32, 32, batch, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    }
+    const fe_t* tw = nullptr;
+    B2R_TRY(ntt_get_twiddles(ctx, omega, log_n, &tw));
+
+    int npass = (log_n + 8) / 9;
+    int S[4];
+    {
+        int base = log_n / npass, extra = log_n % npass;
+        for (int p = 0; p < npass; p++) S[p] = base + (p < extra ? 1 : 0);
+    }
+    // ping-pong: pass p reads buf[p&1], writes the other; arrange that the last pass lands in `out`
+    fe_t* tmp = nullptr;
+    if (npass > 1 || in == out) {
+        B2R_TRY(scratch_get(ctx, SC_NTT_PING, batch * n * sizeof(fe_t), (void**)&tmp));
+    }
+    fe_t n_inv = Fr::zero();
+    fe_t zeta = fr_zeta(), zeta2 = Fr::sqr(zeta);
+    if (mode == MODE_INV || mode == MODE_COSET_INV) n_inv = Fr::inv(fr_from_u64(n));
+
+    const fe_t* src = in;
+    uint64_t src_stride = in_stride;
+    uint32_t src_len = in_len;
+    uint32_t log_s = 0;
+    for (int p = 0; p < npass; p++) {
+        bool last = (p == npass - 1);
+        // destination: last pass -> out; otherwise alternate so that we never write what we read
+        fe_t* dst;
+        uint64_t dst_stride;
+        if (last) {
+            dst = out;
+            dst_stride = out_stride;
+            if (src == out) {  // single pass in place: go through tmp then copy back
+                dst = tmp;
+                dst_stride = n;
+            }
+        } else {
+            // intermediate: use tmp unless src is tmp, then use out (out is free: in was consumed)
+            if (src != tmp) {
+                dst = tmp;
+                dst_stride = n;
+            } else {
+                dst = out;
+                dst_stride = out_stride;
+            }
+        }
+        // if the remaining number of passes would make the last one read from `out`, that is
+        // handled by the in-place branch above (one extra D2D copy).
+        NttPassArgs A;
+        A.x = src;
+        A.y = dst;
+        A.tw = tw;
+        A.in_stride = src_stride;
+        A.out_stride = dst_stride;
+        A.in_len = src_len;
+        A.log_n = log_n;
+        A.log_s = log_s;
+        A.pre = 0;
+        A.post = 0;
+        for (int j = 0; j < 3; j++) A.pre3[j] = A.post3[j] = Fr::one();
+        if (p == 0 && mode == MODE_COSET_FWD) {
+            A.pre = 1;
+            A.pre3[1] = zeta;
+            A.pre3[2] = zeta2;
+        }
+        if (last && mode == MODE_INV) {
+            A.post = 1;
+            A.post3[0] = A.post3[1] = A.post3[2] = n_inv;
+        }
+        if (last && mode == MODE_COSET_INV) {
+            A.post = 1;
+            A.post3[0] = n_inv;
+            A.post3[1] = Fr::mul(n_inv, zeta2);
+            A.post3[2] = Fr::mul(n_inv, zeta);
+        }
+        uint32_t log_cols = log_n - S[p];
+        uint32_t log_c = (S[p] >= 9) ? 2 : 3;
+        if (log_c > log_cols) log_c = log_cols;
+        if (p > 0 && log_c > log_s) log_c = log_s;
+        A.log_c = log_c;
+        size_t smem = ((size_t)sizeof(fe_t) << S[p]) << log_c;
+        ntt_kernel_t kern = pass_kernel(S[p]);
+        if (smem > 48 * 1024) B2R_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(1u << (log_cols - log_c), (unsigned)batch);
+        kern<<<grid, 256, smem, ctx->stream>>>(A);
+        B2R_LAUNCH_CHECK(ctx);
+        if (last && dst != out) {
+            B2R_CUDA(ctx, cudaMemcpy2DAsync(out, out_stride * 32, dst, dst_stride * 32, n * 32, batch, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        src = dst;
+        src_stride = dst_stride;
+        src_len = (uint32_t)n;
+        log_s += S[p];
+    }
+    return 0;
+}
+
+static inline fe_t fe_from_abi(const b2r_fr* p) {
+    fe_t r;
+    for (int i = 0; i < 4; i++) {
+        r.l[2 * i] = (uint32_t)p->l[i];
+        r.l[2 * i + 1] = (uint32_t)(p->l[i] >> 32);
+    }
+    return r;
+}
+
+// host-buffer wrapper: stage through the SC_STAGE arena
+static int32_t ntt_host(b2r_ctx* ctx, const b2r_fr* in, uint32_t in_len, b2r_fr* out, const fe_t& omega,
+                        uint32_t log_n, int mode) {
+    size_t n = (size_t)1 << log_n;
+    fe_t* d = nullptr;
+    B2R_TRY(scratch_get(ctx, SC_STAGE, n * sizeof(fe_t), (void**)&d));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d, in, (size_t)in_len * 32, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_TRY(ntt_run(ctx, d, n, in_len, d, n, 1, omega, log_n, mode));
+    B2R_CUDA(ctx, cudaMemcpyAsync(out, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace b2r
+
+using namespace b2r;
+
+extern "C" {
+
+int32_t b2r_ntt_fr(b2r_ctx* ctx, b2r_fr* a, const b2r_fr* omega, uint32_t log_n) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!a || !omega) return fail(ctx, B2R_ERR_INVALID, "ntt: null pointer");
+    if (log_n > 27) return fail(ctx, B2R_ERR_INVALID, "ntt: log_n > 27");
+    return ntt_host(ctx, a, 1u << log_n, a, fe_from_abi(omega), log_n, MODE_PLAIN);
+}
+int32_t b2r_ntt_fr_dev(b2r_ctx* ctx, b2r_fr* a_dev, const b2r_fr* omega_host, uint32_t log_n) {
+    return b2r_ntt_fr_batch_dev(ctx, a_dev, 1, omega_host, log_n);
+}
+int32_t b2r_ntt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, const b2r_fr* omega_host, uint32_t log_n) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!a_dev || !omega_host) return fail(ctx, B2R_ERR_INVALID, "ntt: null pointer");
+    uint64_t n = 1ull << log_n;
+    return ntt_run(ctx, (fe_t*)a_dev, n, (uint32_t)n, (fe_t*)a_dev, n, batch, fe_from_abi(omega_host), log_n, MODE_PLAIN);
+}
+int32_t b2r_intt_fr(b2r_ctx* ctx, b2r_fr* a, uint32_t k) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!a) return fail(ctx, B2R_ERR_INVALID, "intt: null pointer");
+    if (k > 27) return fail(ctx, B2R_ERR_INVALID, "intt: k > 27");
+    return ntt_host(ctx, a, 1u << k, a, Fr::inv(fr_omega(k)), k, MODE_INV);
+}
+int32_t b2r_intt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, uint32_t k) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!a_dev) return fail(ctx, B2R_ERR_INVALID, "intt: null pointer");
+    if (k > 27) return fail(ctx, B2R_ERR_INVALID, "intt: k > 27");
+    uint64_t n = 1ull << k;
+    return ntt_run(ctx, (fe_t*)a_dev, n, (uint32_t)n, (fe_t*)a_dev, n, batch, Fr::inv(fr_omega(k)), k, MODE_INV);
+}
+int32_t b2r_coset_ntt_fr(b2r_ctx* ctx, const b2r_fr* coeffs, uint32_t k, uint32_t ext_k, b2r_fr* out) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!coeffs || !out) return fail(ctx, B2R_ERR_INVALID, "coset_ntt: null pointer");
+    if (ext_k > 27 || k > ext_k) return fail(ctx, B2R_ERR_INVALID, "coset_ntt: need k <= ext_k <= 27");
+    return ntt_host(ctx, coeffs, 1u << k, out, fr_omega(ext_k), ext_k, MODE_COSET_FWD);
+}
+int32_t b2r_coset_ntt_fr_batch_dev(b2r_ctx* ctx, const b2r_fr* coeffs_dev, size_t batch, uint32_t k, uint32_t ext_k,
+                                   b2r_fr* out_dev) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!coeffs_dev || !out_dev) return fail(ctx, B2R_ERR_INVALID, "coset_ntt: null pointer");
+    if (ext_k > 27 || k > ext_k) return fail(ctx, B2R_ERR_INVALID, "coset_ntt: need k <= ext_k <= 27");
+    if ((const void*)coeffs_dev == (void*)out_dev && k != ext_k)
+        return fail(ctx, B2R_ERR_INVALID, "coset_ntt: in place needs k == ext_k");
+    return ntt_run(ctx, (const fe_t*)coeffs_dev, 1ull << k, 1u << k, (fe_t*)out_dev, 1ull << ext_k, batch,
+                   fr_omega(ext_k), ext_k, MODE_COSET_FWD);
+}
+int32_t b2r_coset_intt_fr(b2r_ctx* ctx, b2r_fr* a, uint32_t ext_k) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!a) return fail(ctx, B2R_ERR_INVALID, "coset_intt: null pointer");
+    if (ext_k > 27) return fail(ctx, B2R_ERR_INVALID, "coset_intt: ext_k > 27");
+    return ntt_host(ctx, a, 1u << ext_k, a, Fr::inv(fr_omega(ext_k)), ext_k, MODE_COSET_INV);
+}
+int32_t b2r_coset_intt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, uint32_t ext_k) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!a_dev) return fail(ctx, B2R_ERR_INVALID, "coset_intt: null pointer");
+    if (ext_k > 27) return fail(ctx, B2R_ERR_INVALID, "coset_intt: ext_k > 27");
+    uint64_t n = 1ull << ext_k;
+    return ntt_run(ctx, (fe_t*)a_dev, n, (uint32_t)n, (fe_t*)a_dev, n, batch, Fr::inv(fr_omega(ext_k)), ext_k,
+                   MODE_COSET_INV);
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+/* libb2rsa - B200-native hot paths for the halo2-rsa prover, C ABI.
+ *
+ * The reference (SoraSuegami/halo2-rsa @ 86358fa) has no FFI of its own: its two
+ * data-parallel hot paths are reached through Rust generics.  Each entry point below
+ * names the reference interface it replaces; INTEGRATION.md shows the Rust `extern "C"`
+ * binding and the ctypes binding used by this repo's tests.
+ *
+ * Conventions
+ *   - every function returns int32_t: 0 = ok, < 0 = b2r_status error (never aborts,
+ *     never unwinds); b2r_last_error(ctx) gives the message of the last failure.
+ *   - element memory format = halo2curves bn256 in-memory format:
+ *       b2r_fr / b2r_fq : 4 x uint64_t little-endian limbs, Montgomery form (R = 2^256)
+ *       b2r_g1_affine   : { fq x; fq y }  64 bytes, identity = (0, 0)
+ *       b2r_g1          : { fq x; fq y; fq z }  96 bytes, Jacobian; identity z = 0
+ *     so a Rust &[Fr] / &[G1Affine] can be passed as a raw pointer.
+ *   - functions without suffix take HOST pointers, copy in/out, and return when the
+ *     result is in the caller's buffer (what the reference's synchronous calls do).
+ *     `_dev` variants take DEVICE pointers, enqueue on the context's stream and return
+ *     immediately (b2r_ctx_sync to wait).  They are what a resident prover pipeline and
+ *     bench.py's device-timed leg use.
+ *   - a context is bound to one device and one stream; calls on one context must not be
+ *     made concurrently from several threads (use one context per thread).
+ */
+#ifndef B2RSA_H
+#define B2RSA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } b2r_fr;
+typedef struct { uint64_t l[4]; } b2r_fq;
+typedef struct { b2r_fq x, y; } b2r_g1_affine;
+typedef struct { b2r_fq x, y, z; } b2r_g1;
+
+typedef struct b2r_ctx b2r_ctx;
+typedef struct b2r_prog b2r_prog;   /* a recorded witness program (static circuit layout) */
+typedef struct b2r_bases b2r_bases; /* a resident, pre-processed MSM base set */
+
+enum b2r_status {
+    B2R_OK = 0,
+    B2R_ERR_INVALID = -1,   /* bad argument (shape, null, range) */
+    B2R_ERR_CUDA = -2,      /* CUDA runtime failure (message in b2r_last_error) */
+    B2R_ERR_NO_DEVICE = -3, /* no usable sm_100 device: the library has no CPU fallback */
+    B2R_ERR_NOMEM = -4,
+    B2R_ERR_LAYOUT = -5,    /* circuit does not fit 2^k rows */
+    B2R_ERR_SYNTH = -6      /* witness synthesis failed (reference would panic / Err) */
+};
+
+/* ---- context ------------------------------------------------------------------------ */
+int32_t b2r_ctx_create(int32_t device, b2r_ctx** out);
+int32_t b2r_ctx_destroy(b2r_ctx* ctx);
+/* use an externally owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+int32_t b2r_ctx_set_stream(b2r_ctx* ctx, void* cuda_stream);
+int32_t b2r_ctx_sync(b2r_ctx* ctx);
+const char* b2r_last_error(const b2r_ctx* ctx);
+const char* b2r_version(void);
+/* number of kernel launches this context has enqueued so far (bench.py `gpu_launches`) */
+uint64_t b2r_launch_count(const b2r_ctx* ctx);
+
+/* plain device memory helpers so a host language needs no CUDA binding of its own */
+int32_t b2r_dev_alloc(b2r_ctx* ctx, size_t bytes, void** dptr);
+int32_t b2r_dev_free(b2r_ctx* ctx, void* dptr);
+int32_t b2r_h2d(b2r_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int32_t b2r_d2h(b2r_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- NTT over Fr -------------------------------------------------------------------
+ * Replaces halo2_proofs::arithmetic::best_fft(a: &mut [Fr], omega: Fr, log_n: u32)
+ * (third-party crate, reached from reference benches/bench.rs:321-329 via create_proof ->
+ * EvaluationDomain::{lagrange_to_coeff, coeff_to_extended, extended_to_coeff}).
+ * Natural order in and out, in place, any primitive 2^log_n-th root `omega`. */
+int32_t b2r_ntt_fr(b2r_ctx* ctx, b2r_fr* a, const b2r_fr* omega, uint32_t log_n);
+int32_t b2r_ntt_fr_dev(b2r_ctx* ctx, b2r_fr* a_dev, const b2r_fr* omega_host, uint32_t log_n);
+/* batched: `batch` independent vectors, contiguous, 2^log_n elements each */
+int32_t b2r_ntt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, const b2r_fr* omega_host,
+                             uint32_t log_n);
+
+/* EvaluationDomain::lagrange_to_coeff: iFFT over the 2^k domain (omega_k^-1, then 1/n). */
+int32_t b2r_intt_fr(b2r_ctx* ctx, b2r_fr* a, uint32_t k);
+int32_t b2r_intt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, uint32_t k);
+/* EvaluationDomain::coeff_to_extended: 2^k coefficients -> 2^ext_k evaluations on the
+ * coset ZETA*<omega_ext> (coefficient i scaled by ZETA^(i mod 3), zero padded, FFT). */
+int32_t b2r_coset_ntt_fr(b2r_ctx* ctx, const b2r_fr* coeffs, uint32_t k, uint32_t ext_k, b2r_fr* out);
+int32_t b2r_coset_ntt_fr_batch_dev(b2r_ctx* ctx, const b2r_fr* coeffs_dev, size_t batch, uint32_t k,
+                                   uint32_t ext_k, b2r_fr* out_dev);
+/* EvaluationDomain::extended_to_coeff: inverse of the above on all 2^ext_k values. */
+int32_t b2r_coset_intt_fr(b2r_ctx* ctx, b2r_fr* a, uint32_t ext_k);
+int32_t b2r_coset_intt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, uint32_t ext_k);
+
+/* ---- MSM over BN254 G1 -------------------------------------------------------------
+ * Replaces halo2_proofs::arithmetic::best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1
+ * reached through ParamsKZG::{commit, commit_lagrange} (reference benches/bench.rs:235,
+ * 321-329).  Bases are made resident once (ParamsKZG::g / g_lagrange never change):
+ * registration builds the per-window multiples 2^(c*j) * P_i so that one MSM needs a
+ * single bucket set and no window-combining doublings. */
+int32_t b2r_bases_register(b2r_ctx* ctx, const b2r_g1_affine* bases_host, size_t n, b2r_bases** out);
+int32_t b2r_bases_free(b2r_ctx* ctx, b2r_bases* bases);
+/* out = sum_i scalars[i] * bases[i], i < n <= registered size.  The point is returned
+ * normalised (z = 1), identity as z = 0: Jacobian coordinates are not canonical, affine
+ * ones are, and the reference converts to affine right after (commit -> to_affine). */
+int32_t b2r_msm_g1(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars, size_t n, b2r_g1* out);
+/* `m` scalar vectors of length n sharing one base set -> m affine points
+ * (one call per batch of advice/lookup/permutation columns) */
+int32_t b2r_msm_g1_batch(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars, size_t m,
+                         size_t n, b2r_g1_affine* out);
+int32_t b2r_msm_g1_batch_dev(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars_dev,
+                             size_t m, size_t n, b2r_g1_affine* out_dev);
+
+/* ---- RSA witness synthesis ---------------------------------------------------------
+ * Replaces the witness side of Circuit::synthesize for the reference's pkcs1v15 circuit
+ * (benches/bench.rs:132-225, SHA-disabled branch) = RSAChip::verify_pkcs1v15_signature
+ * (src/chip.rs:128-199) -> BigIntChip::{assert_in_field, pow_mod_fixed_exp, mul_mod, mul,
+ * is_equal_muled, ...} (src/big_integer/chip.rs).  The call sequence is data independent,
+ * so it is recorded once into a program and replayed on the GPU for a batch. */
+int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_le, size_t e_len,
+                              uint32_t k, b2r_prog** out);
+int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog* prog);
+/* rows used by the layout (must be <= 2^k - blinding rows), number of recorded values */
+int32_t b2r_prog_info(const b2r_prog* prog, uint64_t* rows_used, uint64_t* num_values,
+                      uint64_t* num_levels);
+/* n_limbs, sig_limbs: batch x (bits_len/64) little-endian 64-bit limbs; hash_limbs:
+ * batch x 4.  advice: batch x 5 x 2^k Fr, column-major per instance (HOST pointer);
+ * is_valid: batch bytes (the value of the circuit's final is_valid cell).
+ * blind_seed != 0 fills the last 6 rows of every column with a seeded stream (the rows
+ * halo2's create_proof fills from its RNG); 0 leaves them zero. */
+int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs,
+                              const uint64_t* sig_limbs, const uint64_t* hash_limbs, size_t batch,
+                              uint64_t blind_seed, b2r_fr* advice, uint8_t* is_valid);
+int32_t b2r_rsa_witness_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev,
+                                  const uint64_t* sig_limbs_dev, const uint64_t* hash_limbs_dev,
+                                  size_t batch, uint64_t blind_seed, b2r_fr* advice_dev,
+                                  uint8_t* is_valid_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2RSA_H */

@@ -1,0 +1,91 @@
+"""GPU parity: Pippenger MSM (C ABI) against the oracle's mathematical definition
+(sum_i s_i * P_i, oracle/bn254.py) - SURVEY.md 8 row a13 (best_multiexp).  Affine output is
+canonical, so equality is bit-exact."""
+import numpy as np
+import pytest
+
+import bn254 as O
+from util import fr_to_np, g1_to_np, np_jac_to_g1, np_to_g1
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bases_4096(ctx):
+    pts = O.g1_multiples(4096)
+    return pts, ctx.bases_register(g1_to_np(pts))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 257])
+def test_msm_small_vs_naive(ctx, bases_4096, n):
+    pts, bs = bases_4096
+    sc = O.fr_stream(0x5EED + n, n)
+    got = np_jac_to_g1(ctx.msm(bs, fr_to_np(sc)))
+    assert got == O.msm_naive(sc, pts[:n])
+
+
+def test_msm_closed_form_4096(ctx, bases_4096):
+    # bases (i+1)G  =>  MSM = (sum s_i (i+1)) G
+    pts, bs = bases_4096
+    sc = O.fr_stream(99, 4096)
+    got = np_jac_to_g1(ctx.msm(bs, fr_to_np(sc)))
+    want = O.g1_mul(O.G1_GEN, sum(s * (i + 1) for i, s in enumerate(sc)) % O.R_MOD)
+    assert got == want
+
+
+def test_msm_edge_scalars(ctx, bases_4096):
+    pts, bs = bases_4096
+    n = 64
+    cases = {
+        "zeros": [0] * n,
+        "ones": [1] * n,                       # every point in the same bucket
+        "minus_one": [O.R_MOD - 1] * n,        # top window / signed-digit carry path
+        "cancel": [5, O.R_MOD - 5] + [0] * (n - 2),
+        "pow2": [1 << (4 * i) for i in range(n)][:n],
+        "window_edges": [(1 << 15), (1 << 15) + 1, (1 << 16) - 1, (1 << 16), (1 << 31), (1 << 253)] + [0] * (n - 6),
+    }
+    for name, sc in cases.items():
+        sc = [s % O.R_MOD for s in sc]
+        got = np_jac_to_g1(ctx.msm(bs, fr_to_np(sc)))
+        assert got == O.msm_naive(sc, pts[:n]), name
+
+
+def test_msm_repeated_points_doubling_path(ctx):
+    # identical bases force the P+P and P-P exceptional cases inside a bucket
+    g = O.G1_GEN
+    pts = [g, g, g, O.g1_neg(g), None, O.g1_mul(g, 65536), O.g1_mul(g, 65536)]
+    bs = ctx.bases_register(g1_to_np(pts))
+    for sc in ([7, 7, 7, 7, 3, 1, 1], [1, 1, 0, 2, 9, 0, 0], [65536, 0, 0, 0, 0, 1, 0], [3, 0, 0, 3, 0, 0, 0]):
+        got = np_jac_to_g1(ctx.msm(bs, fr_to_np(sc)))
+        assert got == O.msm_naive(sc, pts)
+    bs.free()
+
+
+def test_msm_batch_skewed_like_advice(ctx, bases_4096):
+    """advice-column-like scalars: mostly 0/1, bytes, 64-bit limbs, a few full-size"""
+    pts, bs = bases_4096
+    n, m = 4096, 3
+    rows = []
+    for v in range(m):
+        raw = O.fr_stream(200 + v, n)
+        col = []
+        for i, x in enumerate(raw):
+            sel = x % 10
+            col.append(0 if sel < 4 else 1 if sel < 6 else (x >> 20) % 256 if sel < 8 else (x >> 30) % (1 << 64) if sel < 9 else x)
+        rows.append(col)
+    arr = np.stack([fr_to_np(c) for c in rows])
+    got = np_to_g1(ctx.msm_batch(bs, arr))
+    for v in range(m):
+        want = O.g1_mul(O.G1_GEN, sum(s * (i + 1) for i, s in enumerate(rows[v])) % O.R_MOD)
+        assert got[v] == want
+
+
+def test_msm_2p16_closed_form(ctx):
+    n = 1 << 16
+    pts = O.g1_multiples(n)
+    bs = ctx.bases_register(g1_to_np(pts))
+    sc = O.fr_stream(0x5EED, n)
+    got = np_jac_to_g1(ctx.msm(bs, fr_to_np(sc)))
+    want = O.g1_mul(O.G1_GEN, sum(s * (i + 1) for i, s in enumerate(sc)) % O.R_MOD)
+    assert got == want
+    bs.free()
