@@ -1,0 +1,156 @@
+"""TEST INFRASTRUCTURE ONLY - ctypes loader for the C oracle (oracle/*.c).
+
+Used by tests/ as the full-size checker and by bench.py as the timed CPU baseline
+("port": this repo's restatement of the reference's CPU algorithms; the Rust reference
+cannot be built in this image).  Never imported by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(LIB)
+            for f in os.listdir(_HERE) if f.endswith((".c", ".h"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+    return _lib
+
+
+def _p(a):
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+def ncores():
+    return os.cpu_count() or 1
+
+
+def best_fft(a: np.ndarray, omega: np.ndarray, log_n: int, threads: int = 0) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    omega = np.ascontiguousarray(omega, dtype=np.uint64)
+    lib().orc_best_fft(_p(a), _p(omega), C.c_uint(log_n), C.c_int(threads or ncores()))
+    return a
+
+
+def lagrange_to_coeff(a, k, threads=0):
+    a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    lib().orc_lagrange_to_coeff(_p(a), C.c_uint(k), C.c_int(threads or ncores()))
+    return a
+
+
+def coeff_to_extended(co, k, ext_k, threads=0):
+    co = np.ascontiguousarray(co, dtype=np.uint64)
+    out = np.empty((1 << ext_k, 4), dtype=np.uint64)
+    lib().orc_coeff_to_extended(_p(co), C.c_uint(k), C.c_uint(ext_k), _p(out), C.c_int(threads or ncores()))
+    return out
+
+
+def extended_to_coeff(a, ext_k, threads=0):
+    a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    lib().orc_extended_to_coeff(_p(a), C.c_uint(ext_k), C.c_int(threads or ncores()))
+    return a
+
+
+def best_multiexp(scalars: np.ndarray, bases: np.ndarray, threads: int = 0) -> np.ndarray:
+    """-> uint64[8] affine (Montgomery), identity = zeros"""
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    bases = np.ascontiguousarray(bases, dtype=np.uint64)
+    n = scalars.shape[0]
+    assert bases.shape[0] >= n
+    out = np.zeros(8, dtype=np.uint64)
+    lib().orc_best_multiexp(_p(scalars), _p(bases), C.c_size_t(n), C.c_int(threads or ncores()), _p(out))
+    return out
+
+
+def g1_multiples(n: int, threads: int = 0) -> np.ndarray:
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().orc_g1_multiples(_p(out), C.c_size_t(n), C.c_int(threads or ncores()))
+    return out
+
+
+def g1_scalar_muls(scalars: np.ndarray, threads: int = 0) -> np.ndarray:
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    out = np.zeros((scalars.shape[0], 8), dtype=np.uint64)
+    lib().orc_g1_scalar_muls(_p(scalars), _p(out), C.c_size_t(scalars.shape[0]), C.c_int(threads or ncores()))
+    return out
+
+
+# ---- hot path (a): witness synthesis oracle (oracle/rsa_witness.c) ---------------------------
+class RsaTable:
+    """One synthesized circuit table: the oracle's Circuit::synthesize for the bench circuit
+    (reference benches/bench.rs:132-225) + a MockProver-style checker."""
+
+    def __init__(self, bits_len: int, k: int):
+        L = lib()
+        L.orc_table_new.restype = C.c_void_p
+        L.orc_table_rows.restype = C.c_uint64
+        L.orc_check.restype = C.c_long
+        self.k, self.bits_len, self.nl = k, bits_len, bits_len // 64
+        self.h = C.c_void_p(L.orc_table_new(C.c_uint(k), C.c_int(64), C.c_int(self.nl)))
+
+    def synthesize(self, n_limbs, sig_limbs, hash_limbs, e: int = 65537) -> int:
+        """-> 1/0 = value of is_valid, -1 = the reference would have panicked"""
+        e_le = np.frombuffer(e.to_bytes((e.bit_length() + 7) // 8, "little"), dtype=np.uint8).copy()
+        n_limbs = np.ascontiguousarray(n_limbs, dtype=np.uint64)
+        sig_limbs = np.ascontiguousarray(sig_limbs, dtype=np.uint64)
+        hash_limbs = np.ascontiguousarray(hash_limbs, dtype=np.uint64)
+        assert n_limbs.shape == (self.nl,) and sig_limbs.shape == (self.nl,) and hash_limbs.shape == (4,)
+        return int(lib().orc_rsa_synthesize(self.h, C.c_int(self.bits_len), _p(e_le), C.c_int(e_le.size),
+                                            _p(n_limbs), _p(sig_limbs), _p(hash_limbs)))
+
+    def advice(self) -> np.ndarray:
+        out = np.empty((5, 1 << self.k, 4), dtype=np.uint64)
+        lib().orc_table_advice(self.h, _p(out))
+        return out
+
+    def rows(self) -> int:
+        return int(lib().orc_table_rows(self.h))
+
+    def check(self):
+        """-> (number of violated constraints, description of the first few)"""
+        buf = C.create_string_buffer(4096)
+        bad = lib().orc_check(self.h, buf, C.c_size_t(4096))
+        return int(bad), buf.value.decode()
+
+    def free(self):
+        if self.h:
+            lib().orc_table_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def int_to_limbs64(x: int, n: int) -> np.ndarray:
+    return np.array([(x >> (64 * i)) & ((1 << 64) - 1) for i in range(n)], dtype=np.uint64)
+
+
+def rsa_synthesize(bits_len: int, k: int, n: int, sig: int, hashed: int, e: int = 65537):
+    """convenience: integers in -> (is_valid, advice uint64[5,2^k,4], rows, violations, msg)"""
+    t = RsaTable(bits_len, k)
+    nl = bits_len // 64
+    v = t.synthesize(int_to_limbs64(n, nl), int_to_limbs64(sig, nl), int_to_limbs64(hashed, 4), e)
+    bad, msg = t.check()
+    out = (v, t.advice(), t.rows(), bad, msg)
+    t.free()
+    return out

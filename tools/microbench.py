@@ -36,7 +36,10 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     a = ap.parse_args()
     ctx = b2rsa.Context(0)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # torch's default stream has handle 0 (== "own stream" for b2r_ctx_set_stream): time on a side stream
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    ctx.set_stream(side.cuda_stream)
     for L in a.ntt:
         n = 1 << L
         x = torch.from_numpy(random_fr_np(n, L).view(np.int64)).cuda()
