@@ -1,10 +1,646 @@
-// placeholder until the witness path lands (replaced in the next milestone)
+// RSA witness synthesis on the GPU: replay of a recorded circuit program for a batch.
+//
+// Replaces the witness side of the reference's Circuit::synthesize for the pkcs1v15
+// circuit (benches/bench.rs:132-225 -> src/chip.rs:128-199 -> src/big_integer/chip.rs).
+// circuit.hpp records the call sequence once (it is data independent); here
+//   k_witness_eval  one CTA per proof instance walks the value graph level by level
+//                   (nodes are sorted by dependency depth, so a level is a contiguous
+//                   id range evaluated by all threads, __syncthreads between levels).
+//                   Field values are kept in Montgomery form = halo2curves' memory format.
+//                   The multi-limb BigUint steps (q, r = divrem(a*b, n), chip.rs:556-567;
+//                   a - b, chip.rs:1297-1300) are "big ops" evaluated in shared memory.
+//   k_witness_emit  gathers values into the 5 advice columns (column-major, 2^k rows,
+//                   unassigned cells = 0, optional seeded blinding rows): pure HBM write
+//                   stream, 5 * 2^k * 32 B per proof.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "circuit.hpp"
 #include "ctx.hpp"
+
 using namespace b2r;
-extern "C" {
-int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t, const uint8_t*, size_t, uint32_t, b2r_prog**) { return fail(ctx, B2R_ERR_INVALID, "witness path not built"); }
-int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog*) { return fail(ctx, B2R_ERR_INVALID, "witness path not built"); }
-int32_t b2r_prog_info(const b2r_prog*, uint64_t*, uint64_t*, uint64_t*) { return B2R_ERR_INVALID; }
-int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog*, const uint64_t*, const uint64_t*, const uint64_t*, size_t, uint64_t, b2r_fr*, uint8_t*) { return fail(ctx, B2R_ERR_INVALID, "witness path not built"); }
-int32_t b2r_rsa_witness_batch_dev(b2r_ctx* ctx, const b2r_prog*, const uint64_t*, const uint64_t*, const uint64_t*, size_t, uint64_t, b2r_fr*, uint8_t*) { return fail(ctx, B2R_ERR_INVALID, "witness path not built"); }
+using namespace b2r::circuit;
+
+struct LevelRange {
+    uint32_t start, end;    // node ids
+    uint32_t bstart, bend;  // range in big_nodes
+};
+
+struct b2r_prog {
+    uint32_t bits_len = 0, num_limbs = 0, k = 0;
+    uint32_t rows_used = 0, num_values = 0, num_levels = 0;
+    int32_t is_valid_vid = -1;
+    uint32_t num_inputs = 0;
+    // device
+    Node* d_nodes = nullptr;
+    LevelRange* d_levels = nullptr;
+    uint32_t* d_big_nodes = nullptr;
+    BigOp* d_big_ops = nullptr;
+    uint32_t* d_big_inputs = nullptr;
+    fe_t* d_consts = nullptr;
+    int32_t* d_cellmap = nullptr;  // [5][2^k]
+    uint32_t max_big_words = 0;
+    // host copies kept for keygen / inspection
+    std::vector<std::array<uint32_t, NUM_FIXED>> fixed;
+    std::vector<std::array<uint8_t, 4>> range_tags;
+    std::vector<std::array<uint32_t, 4>> copies;
+    std::vector<U256> constants;
+};
+
+namespace b2r {
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ fe_t ldv(const fe_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fe_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
 }
+__device__ __forceinline__ void stv(fe_t* p, const fe_t& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ fe_t fe_from_u64_dev(uint64_t v) {
+    fe_t c = Fr::zero();
+    c.l[0] = (uint32_t)v;
+    c.l[1] = (uint32_t)(v >> 32);
+    return Fr::to_mont(c);
+}
+// canonical integer ops on 8 x u32
+__device__ __forceinline__ fe_t int_shr(const fe_t& x, uint32_t b) {
+    fe_t r = Fr::zero();
+    uint32_t ws = b >> 5, bs = b & 31;
+    for (int i = 0; i < 8; i++) {
+        uint32_t src = i + ws;
+        uint32_t lo = src < 8 ? x.l[src] : 0, hi = src + 1 < 8 ? x.l[src + 1] : 0;
+        r.l[i] = bs ? ((lo >> bs) | (hi << (32 - bs))) : lo;
+    }
+    return r;
+}
+__device__ __forceinline__ fe_t int_lowbits(const fe_t& x, uint32_t b) {
+    fe_t r;
+    for (int i = 0; i < 8; i++) {
+        uint32_t lo = 32 * i;
+        if (b >= lo + 32) r.l[i] = x.l[i];
+        else if (b <= lo) r.l[i] = 0;
+        else r.l[i] = x.l[i] & ((1u << (b - lo)) - 1);
+    }
+    return r;
+}
+__device__ __forceinline__ fe_t int_clearlow(const fe_t& x, uint32_t b) {
+    fe_t r;
+    for (int i = 0; i < 8; i++) {
+        uint32_t lo = 32 * i;
+        if (b >= lo + 32) r.l[i] = 0;
+        else if (b <= lo) r.l[i] = x.l[i];
+        else r.l[i] = x.l[i] & ~((1u << (b - lo)) - 1);
+    }
+    return r;
+}
+
+// ---- big ops: BigUint arithmetic in shared memory, u32 limbs ------------------------------------
+// to_big_uint (src/big_integer/mod.rs:348-359): sum_i int(limb_i) << (width * i); limbs are field
+// elements and may exceed `width` bits, so this is a real multi-word accumulation.
+__device__ void big_gather(const fe_t* values, const uint32_t* ids, uint32_t n, uint32_t width, uint32_t* out, uint32_t nwords) {
+    for (uint32_t i = 0; i < nwords; i++) out[i] = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        fe_t c = Fr::from_mont(ldv(values + ids[i]));
+        uint32_t bit = width * i, ws = bit >> 5, bs = bit & 31;
+        uint64_t carry = 0;
+        for (uint32_t j = 0; j < 9; j++) {
+            uint32_t lo = j < 8 ? c.l[j] : 0, prev = j > 0 ? c.l[j - 1] : 0;
+            uint32_t w = bs ? ((lo << bs) | (prev >> (32 - bs))) : lo;
+            if (ws + j >= nwords) break;
+            carry += (uint64_t)out[ws + j] + w;
+            out[ws + j] = (uint32_t)carry;
+            carry >>= 32;
+        }
+        for (uint32_t j = ws + 9; carry && j < nwords; j++) {
+            carry += out[j];
+            out[j] = (uint32_t)carry;
+            carry >>= 32;
+        }
+    }
+}
+__device__ __forceinline__ uint32_t big_len(const uint32_t* a, uint32_t n) {
+    while (n > 0 && a[n - 1] == 0) n--;
+    return n;
+}
+// Knuth D on normalised copies; un has m+n+1 words, vn has n words (n >= 2); q gets m+1 words
+__device__ void big_divrem(uint32_t* un, uint32_t ulen, const uint32_t* v, uint32_t n, uint32_t* vn, uint32_t* q, uint32_t* rem) {
+    // returns quotient in q[0..ulen-n], remainder in rem[0..n)
+    uint32_t s = __clz(v[n - 1]);
+    for (uint32_t i = n - 1; i > 0; i--) vn[i] = s ? ((v[i] << s) | (v[i - 1] >> (32 - s))) : v[i];
+    vn[0] = v[0] << s;
+    un[ulen] = s ? (un[ulen - 1] >> (32 - s)) : 0;
+    for (uint32_t i = ulen - 1; i > 0; i--) un[i] = s ? ((un[i] << s) | (un[i - 1] >> (32 - s))) : un[i];
+    un[0] = un[0] << s;
+    uint32_t m = ulen - n;
+    for (int32_t j = (int32_t)m; j >= 0; j--) {
+        uint64_t num = ((uint64_t)un[j + n] << 32) | un[j + n - 1];
+        uint64_t qhat = num / vn[n - 1], rhat = num % vn[n - 1];
+        while (qhat >= (1ull << 32) || qhat * vn[n - 2] > ((rhat << 32) | un[j + n - 2])) {
+            qhat--;
+            rhat += vn[n - 1];
+            if (rhat >= (1ull << 32)) break;
+        }
+        int64_t borrow = 0;
+        uint64_t carry = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            uint64_t p = qhat * vn[i] + carry;
+            carry = p >> 32;
+            int64_t t = (int64_t)un[i + j] - borrow - (int64_t)(p & 0xffffffffull);
+            un[i + j] = (uint32_t)t;
+            borrow = t < 0 ? 1 : 0;
+        }
+        int64_t t = (int64_t)un[j + n] - borrow - (int64_t)carry;
+        un[j + n] = (uint32_t)t;
+        if (t < 0) {
+            qhat--;
+            uint64_t c = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                c += (uint64_t)un[i + j] + vn[i];
+                un[i + j] = (uint32_t)c;
+                c >>= 32;
+            }
+            un[j + n] += (uint32_t)c;
+        }
+        q[j] = (uint32_t)qhat;
+    }
+    for (uint32_t i = 0; i < n; i++) rem[i] = s ? ((un[i] >> s) | (un[i + 1] << (32 - s))) : un[i];
+}
+
+// one thread evaluates one big op; `sh` is a shared scratch of 6 * W words
+__device__ bool big_eval(const BigOp& op, const uint32_t* ids, fe_t* values, uint32_t out0, uint32_t* sh, uint32_t W) {
+    const uint32_t lw = op.limb_width;
+    uint32_t* A = sh;           // W
+    uint32_t* Bv = sh + W;      // W
+    uint32_t* Nv = sh + 2 * W;  // W
+    uint32_t* PR = sh + 3 * W;  // 2W + 2 (product / dividend)
+    uint32_t* Q = sh + 5 * W + 2;  // W + 2
+    uint32_t* VN = Q + W + 2;      // W
+    bool ok = true;
+    big_gather(values, ids, op.na, lw, A, W);
+    big_gather(values, ids + op.na, op.nb, lw, Bv, W);
+    if (op.kind == BIG_SUB) {
+        // c = a - b ; a < b panics in the reference (BigUint underflow)
+        int64_t br = 0;
+        for (uint32_t i = 0; i < W; i++) {
+            int64_t t = (int64_t)A[i] - Bv[i] - br;
+            PR[i] = (uint32_t)t;
+            br = t < 0 ? 1 : 0;
+        }
+        if (br) {
+            ok = false;
+            for (uint32_t i = 0; i < W; i++) PR[i] = 0;
+        }
+        for (uint32_t i = 0; i < op.nout; i++) {
+            uint32_t bit = lw * i;  // lw == 64
+            uint64_t v = (uint64_t)PR[bit >> 5] | ((uint64_t)PR[(bit >> 5) + 1] << 32);
+            stv(values + out0 + i, fe_from_u64_dev(v));
+        }
+        return ok;
+    }
+    big_gather(values, ids + op.na + op.nb, op.nn, lw, Nv, W);
+    uint32_t la = big_len(A, W), lb = big_len(Bv, W), ln = big_len(Nv, W);
+    for (uint32_t i = 0; i < 2 * W + 2; i++) PR[i] = 0;
+    for (uint32_t i = 0; i < la; i++) {
+        uint64_t c = 0;
+        uint32_t ai = A[i];
+        for (uint32_t j = 0; j < lb; j++) {
+            c += (uint64_t)ai * Bv[j] + PR[i + j];
+            PR[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        PR[i + lb] = (uint32_t)c;
+    }
+    uint32_t lp = big_len(PR, 2 * W);
+    for (uint32_t i = 0; i < W + 2; i++) Q[i] = 0;
+    // remainder reuses A
+    for (uint32_t i = 0; i < W; i++) A[i] = 0;
+    if (ln == 0) {
+        ok = false;  // division by zero panics in the reference
+    } else if (lp < ln) {
+        for (uint32_t i = 0; i < lp; i++) A[i] = PR[i];
+    } else if (ln == 1) {
+        uint64_t r = 0;
+        for (int32_t i = (int32_t)lp - 1; i >= 0; i--) {
+            uint64_t cur = (r << 32) | PR[i];
+            uint32_t qd = (uint32_t)(cur / Nv[0]);
+            if ((uint32_t)i < W + 2) Q[i] = qd; else if (qd) ok = false;
+            r = cur % Nv[0];
+        }
+        A[0] = (uint32_t)r;
+    } else {
+        if (lp - ln + 1 > W + 2) {
+            ok = false;
+        } else {
+            big_divrem(PR, lp, Nv, ln, VN, Q, A);
+        }
+    }
+    // q must fit nb limbs and r must fit na limbs (asserts at chip.rs:583-584)
+    uint32_t lq = big_len(Q, W + 2), lr = big_len(A, W);
+    if (lq * 32 > op.nb * lw && lq > 0) {
+        uint32_t bits = 32 * (lq - 1) + (32 - __clz(Q[lq - 1]));
+        if (bits > op.nb * lw) ok = false;
+    }
+    if (lr * 32 > op.na * lw && lr > 0) {
+        uint32_t bits = 32 * (lr - 1) + (32 - __clz(A[lr - 1]));
+        if (bits > op.na * lw) ok = false;
+    }
+    for (uint32_t i = 0; i < op.nb; i++) {
+        uint32_t w0 = 2 * i;
+        uint64_t v = (uint64_t)(w0 < W + 2 ? Q[w0] : 0) | ((uint64_t)(w0 + 1 < W + 2 ? Q[w0 + 1] : 0) << 32);
+        stv(values + out0 + i, fe_from_u64_dev(ok ? v : 0));
+    }
+    for (uint32_t i = 0; i < op.na; i++) {
+        uint32_t w0 = 2 * i;
+        uint64_t v = (uint64_t)(w0 < W ? A[w0] : 0) | ((uint64_t)(w0 + 1 < W ? A[w0 + 1] : 0) << 32);
+        stv(values + out0 + op.nb + i, fe_from_u64_dev(ok ? v : 0));
+    }
+    return ok;
+}
+
+struct WitnessArgs {
+    const Node* nodes;
+    const LevelRange* levels;
+    const uint32_t* big_nodes;
+    const BigOp* big_ops;
+    const uint32_t* big_inputs;
+    const fe_t* consts;
+    const uint64_t* n_limbs;
+    const uint64_t* sig_limbs;
+    const uint64_t* hash_limbs;
+    fe_t* values;  // [batch][num_values]
+    uint8_t* is_valid;
+    uint32_t num_levels, num_values, num_limbs, big_words;
+    int32_t is_valid_vid;
+};
+
+__global__ void __launch_bounds__(1024) k_witness_eval(const WitnessArgs A) {
+    extern __shared__ uint32_t sh_big[];
+    __shared__ int sh_err;
+    const uint32_t p = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    fe_t* val = A.values + (size_t)p * A.num_values;
+    if (tid == 0) sh_err = 0;
+    __syncthreads();
+    for (uint32_t lv = 0; lv < A.num_levels; lv++) {
+        const LevelRange L = A.levels[lv];
+        for (uint32_t id = L.start + tid; id < L.end; id += T) {
+            const Node nd = A.nodes[id];
+            fe_t r;
+            switch (nd.op) {
+                case OP_CONST: r = ldv(A.consts + nd.a); break;
+                case OP_INPUT: {
+                    uint32_t w = nd.a, nl = A.num_limbs;
+                    uint64_t v = w < nl ? A.n_limbs[(size_t)p * nl + w]
+                               : w < 2 * nl ? A.sig_limbs[(size_t)p * nl + (w - nl)]
+                                            : A.hash_limbs[(size_t)p * 4 + (w - 2 * nl)];
+                    r = fe_from_u64_dev(v);
+                    break;
+                }
+                case OP_ADD: r = Fr::add(ldv(val + nd.a), ldv(val + nd.b)); break;
+                case OP_SUB: r = Fr::sub(ldv(val + nd.a), ldv(val + nd.b)); break;
+                case OP_MUL: r = Fr::mul(ldv(val + nd.a), ldv(val + nd.b)); break;
+                case OP_MULADD: r = Fr::add(Fr::mul(ldv(val + nd.a), ldv(val + nd.b)), ldv(val + nd.c)); break;
+                case OP_ADDC: r = Fr::add(ldv(val + nd.a), ldv(A.consts + nd.b)); break;
+                case OP_ADD2C: r = Fr::add(Fr::add(ldv(val + nd.a), ldv(val + nd.b)), ldv(A.consts + nd.c)); break;
+                case OP_NOT: r = Fr::sub(Fr::one(), ldv(val + nd.a)); break;
+                case OP_SELECT: {
+                    fe_t c = ldv(val + nd.c);
+                    r = Fr::eq(c, Fr::one()) ? ldv(val + nd.a) : ldv(val + nd.b);
+                    break;
+                }
+                case OP_ISZERO: r = Fr::is_zero(ldv(val + nd.a)) ? Fr::one() : Fr::zero(); break;
+                case OP_INVORONE: {
+                    fe_t x = ldv(val + nd.a);
+                    r = Fr::is_zero(x) ? Fr::one() : Fr::inv(x);
+                    break;
+                }
+                case OP_SHR: r = Fr::to_mont(int_shr(Fr::from_mont(ldv(val + nd.a)), nd.b)); break;
+                case OP_LOWBITS: r = Fr::to_mont(int_lowbits(Fr::from_mont(ldv(val + nd.a)), nd.b)); break;
+                case OP_SUBLIMB: r = Fr::to_mont(int_lowbits(int_shr(Fr::from_mont(ldv(val + nd.a)), nd.b), nd.c)); break;
+                case OP_CLEARLOW: r = Fr::to_mont(int_clearlow(Fr::from_mont(ldv(val + nd.a)), nd.b)); break;
+                default: continue;  // OP_BIG / OP_BIGOUT: written below
+            }
+            stv(val + id, r);
+        }
+        if (tid == 0) {
+            for (uint32_t bi = L.bstart; bi < L.bend; bi++) {
+                uint32_t id = A.big_nodes[bi];
+                const BigOp op = A.big_ops[A.nodes[id].a];
+                if (!big_eval(op, A.big_inputs + op.in_off, val, id + 1, sh_big, A.big_words)) sh_err = 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        uint8_t v = 0xff;
+        if (!sh_err) v = Fr::eq(ldv(val + A.is_valid_vid), Fr::one()) ? 1 : 0;
+        A.is_valid[p] = v;
+    }
+}
+
+// seeded blinding stream (documented in DESIGN.md; restated by tests): splitmix64 over
+// (seed, instance, column, row, word), top two bits cleared, one conditional subtraction of r.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ fe_t blind_value(uint64_t seed, uint32_t p, uint32_t col, uint32_t row) {
+    fe_t r;
+    uint64_t base = splitmix64(seed ^ splitmix64(((uint64_t)p << 32) | ((uint64_t)col << 28) | row));
+    for (int j = 0; j < 4; j++) {
+        uint64_t w = splitmix64(base + j);
+        r.l[2 * j] = (uint32_t)w;
+        r.l[2 * j + 1] = (uint32_t)(w >> 32);
+    }
+    r.l[7] &= 0x3fffffffu;
+    Fr::final_sub(r.l);
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_witness_emit(const int32_t* __restrict__ cellmap, const fe_t* __restrict__ values, uint32_t num_values, uint32_t k,
+               uint32_t usable_rows, uint64_t blind_seed, uint32_t p_base, fe_t* __restrict__ advice) {
+    const uint32_t n = 1u << k;
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t col = blockIdx.y, p = blockIdx.z;
+    if (row >= n) return;
+    fe_t v;
+    if (row >= usable_rows) {
+        v = blind_seed ? blind_value(blind_seed, p_base + p, col, row) : Fr::zero();
+    } else {
+        int32_t id = cellmap[(size_t)col * n + row];
+        v = id < 0 ? Fr::zero() : ldv(values + (size_t)p * num_values + id);
+    }
+    stv(advice + ((size_t)p * NUM_ADVICE + col) * n + row, v);
+}
+
+}  // namespace b2r
+
+// ---- program construction (host) ------------------------------------------------------------------
+static fe_t u256_to_mont(const U256& v) {
+    fe_t c;
+    for (int i = 0; i < 4; i++) {
+        c.l[2 * i] = (uint32_t)v.l[i];
+        c.l[2 * i + 1] = (uint32_t)(v.l[i] >> 32);
+    }
+    return Fr::to_mont(c);
+}
+
+template <class T>
+static int32_t upload(b2r_ctx* ctx, const std::vector<T>& v, T** d) {
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    B2R_CUDA(ctx, cudaMalloc((void**)d, bytes));
+    if (!v.empty()) B2R_CUDA(ctx, cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// sorts the recorded nodes by level, renumbers value ids, uploads everything
+static int32_t finalize_program(b2r_ctx* ctx, RegionCtx& rc, AssignedValue is_valid, b2r_prog* prog) {
+    const size_t N = rc.nodes.size();
+    std::vector<uint32_t> order(N);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return rc.level[a] < rc.level[b]; });
+    std::vector<uint32_t> newid(N);
+    for (size_t i = 0; i < N; i++) newid[order[i]] = (uint32_t)i;
+    std::vector<Node> nodes(N);
+    uint32_t nlev = 0;
+    for (size_t i = 0; i < N; i++) nlev = std::max(nlev, rc.level[i] + 1);
+    std::vector<LevelRange> levels(nlev);
+    for (auto& l : levels) l.start = l.end = l.bstart = l.bend = 0;
+    std::vector<uint32_t> big_nodes;
+    for (size_t i = 0; i < N; i++) {
+        Node nd = rc.nodes[order[i]];
+        switch (nd.op) {
+            case OP_ADD: case OP_SUB: case OP_MUL: case OP_ADD2C:
+                nd.a = newid[nd.a]; nd.b = newid[nd.b]; break;
+            case OP_MULADD: case OP_SELECT:
+                nd.a = newid[nd.a]; nd.b = newid[nd.b]; nd.c = newid[nd.c]; break;
+            case OP_ADDC: case OP_NOT: case OP_ISZERO: case OP_INVORONE: case OP_SHR: case OP_LOWBITS: case OP_SUBLIMB: case OP_CLEARLOW:
+                nd.a = newid[nd.a]; break;
+            default: break;
+        }
+        nodes[i] = nd;
+        uint32_t lv = rc.level[order[i]];
+        if (i == 0 || rc.level[order[i - 1]] != lv) {
+            levels[lv].start = (uint32_t)i;
+            levels[lv].bstart = (uint32_t)big_nodes.size();
+        }
+        levels[lv].end = (uint32_t)i + 1;
+        if (nd.op == OP_BIG) big_nodes.push_back((uint32_t)i);
+        levels[lv].bend = (uint32_t)big_nodes.size();
+    }
+    for (auto& id : rc.big_inputs) id = newid[id];
+    const uint32_t n = 1u << prog->k;
+    std::vector<int32_t> cellmap((size_t)NUM_ADVICE * n, -1);
+    for (int c = 0; c < NUM_ADVICE; c++)
+        for (size_t r = 0; r < rc.cell[c].size(); r++)
+            if (rc.cell[c][r] >= 0) cellmap[(size_t)c * n + r] = (int32_t)newid[rc.cell[c][r]];
+    std::vector<fe_t> consts(rc.constants.size());
+    for (size_t i = 0; i < consts.size(); i++) consts[i] = u256_to_mont(rc.constants[i]);
+    uint32_t maxw = 0;
+    for (const auto& op : rc.big_ops) {
+        uint32_t w = std::max(std::max(op.na, op.nb), op.nn) * op.limb_width / 32 + 10;
+        maxw = std::max(maxw, w);
+    }
+    prog->max_big_words = maxw;
+    prog->rows_used = rc.offset;
+    prog->num_values = (uint32_t)N;
+    prog->num_levels = nlev;
+    prog->is_valid_vid = (int32_t)newid[is_valid.vid];
+    B2R_TRY(upload(ctx, nodes, &prog->d_nodes));
+    B2R_TRY(upload(ctx, levels, &prog->d_levels));
+    B2R_TRY(upload(ctx, big_nodes, &prog->d_big_nodes));
+    B2R_TRY(upload(ctx, rc.big_ops, &prog->d_big_ops));
+    B2R_TRY(upload(ctx, rc.big_inputs, &prog->d_big_inputs));
+    B2R_TRY(upload(ctx, consts, &prog->d_consts));
+    B2R_TRY(upload(ctx, cellmap, &prog->d_cellmap));
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    prog->fixed = std::move(rc.fixed);
+    prog->range_tags = std::move(rc.range_tags);
+    prog->copies = std::move(rc.copies);
+    prog->constants = rc.constants;
+    return 0;
+}
+
+static void prog_release(b2r_prog* p) {
+    cudaFree(p->d_nodes);
+    cudaFree(p->d_levels);
+    cudaFree(p->d_big_nodes);
+    cudaFree(p->d_big_ops);
+    cudaFree(p->d_big_inputs);
+    cudaFree(p->d_consts);
+    cudaFree(p->d_cellmap);
+    delete p;
+}
+
+static constexpr uint32_t BLINDING_ROWS = 6;  // cs.blinding_factors() + 1 = 5 + 1 for this circuit
+
+extern "C" {
+
+int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_le, size_t e_len, uint32_t k, b2r_prog** out) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!out || !e_le || e_len == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: null argument");
+    *out = nullptr;
+    if (bits_len < 512 || bits_len > 4096 || bits_len % 64) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: bits_len must be a multiple of 64 in [512, 4096]");
+    if (k < 4 || k > 24) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: k out of range");
+    bool e_nonzero = false;
+    for (size_t i = 0; i < e_len; i++) e_nonzero |= e_le[i] != 0;
+    if (!e_nonzero) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: exponent is zero");
+    b2r_prog* prog = new b2r_prog();
+    prog->bits_len = bits_len;
+    prog->num_limbs = bits_len / 64;
+    prog->k = k;
+    prog->num_inputs = 2 * prog->num_limbs + 4;
+    try {
+        const uint32_t nl = prog->num_limbs;
+        RegionCtx rc((1u << k) - BLINDING_ROWS);
+        // RangeChip::configure with RSAChip::compute_range_lens: distinct non-zero bit lengths, ascending tags
+        std::vector<unsigned> comp, over;
+        RSAChip::compute_range_lens(nl, comp, over);
+        std::vector<unsigned> lens;
+        for (unsigned v : comp) if (v) lens.push_back(v);
+        for (unsigned v : over) if (v) lens.push_back(v);
+        std::sort(lens.begin(), lens.end());
+        lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
+        for (size_t i = 0; i < lens.size(); i++) rc.tag_of_bits[lens[i]] = (int)i + 1;
+
+        RSAChip rsa_chip(bits_len, 5);
+        BigIntChip bigint_chip = rsa_chip.bigint_chip();
+        MainGate main_gate;
+        std::vector<uint8_t> e(e_le, e_le + e_len);
+        // region 1 (bench.rs:145-156): signature, then public key
+        UnassignedInteger sig_u, n_u, hash_u;
+        for (uint32_t i = 0; i < nl; i++) n_u.limbs.push_back(rc.input(i));
+        for (uint32_t i = 0; i < nl; i++) sig_u.limbs.push_back(rc.input(nl + i));
+        for (uint32_t i = 0; i < 4; i++) hash_u.limbs.push_back(rc.input(2 * nl + i));
+        AssignedRSASignature sign = rsa_chip.assign_signature(rc, sig_u);
+        AssignedRSAPublicKey public_key = rsa_chip.assign_public_key(rc, n_u, e);
+        // region 2 (bench.rs:186-211): hashed message, verification
+        AssignedInteger hashed = bigint_chip.assign_integer(rc, hash_u);
+        AssignedValue is_valid = rsa_chip.verify_pkcs1v15_signature(rc, public_key, hashed, sign);
+        // region 3 (bench.rs:213-221)
+        main_gate.assert_one(rc, is_valid);
+        int32_t r = finalize_program(ctx, rc, is_valid, prog);
+        if (r) {
+            prog_release(prog);
+            return r;
+        }
+    } catch (const SynthError& e) {
+        prog_release(prog);
+        return fail(ctx, e.code == -5 ? B2R_ERR_LAYOUT : (e.code == -1 ? B2R_ERR_INVALID : B2R_ERR_SYNTH), e.what());
+    } catch (const std::exception& e) {
+        prog_release(prog);
+        return fail(ctx, B2R_ERR_NOMEM, e.what());
+    }
+    *out = prog;
+    return 0;
+}
+
+int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog* prog) {
+    if (!ctx || !prog) return B2R_ERR_INVALID;
+    cudaStreamSynchronize(ctx->stream);
+    prog_release(prog);
+    return 0;
+}
+
+int32_t b2r_prog_info(const b2r_prog* prog, uint64_t* rows_used, uint64_t* num_values, uint64_t* num_levels) {
+    if (!prog) return B2R_ERR_INVALID;
+    if (rows_used) *rows_used = prog->rows_used;
+    if (num_values) *num_values = prog->num_values;
+    if (num_levels) *num_levels = prog->num_levels;
+    return 0;
+}
+
+static int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
+                           const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev,
+                           uint8_t* is_valid_dev, size_t p_base) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!prog || !n_limbs_dev || !sig_limbs_dev || !hash_limbs_dev || !advice_dev || !is_valid_dev)
+        return fail(ctx, B2R_ERR_INVALID, "rsa_witness: null pointer");
+    if (batch == 0) return 0;
+    const uint32_t n = 1u << prog->k;
+    // value store: process the batch in groups that fit a bounded arena
+    size_t per = (size_t)prog->num_values * sizeof(fe_t);
+    size_t G = std::max<size_t>(1, std::min<size_t>(batch, ((size_t)2 << 30) / per));
+    fe_t* values = nullptr;
+    B2R_TRY(scratch_get(ctx, SC_WIT, G * per, (void**)&values));
+    size_t big_smem = ((size_t)prog->max_big_words * 7 + 16) * sizeof(uint32_t);
+    if (big_smem > 48 * 1024) B2R_CUDA(ctx, cudaFuncSetAttribute(k_witness_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem));
+    for (size_t p0 = 0; p0 < batch; p0 += G) {
+        size_t g = std::min(G, batch - p0);
+        WitnessArgs A;
+        A.nodes = prog->d_nodes;
+        A.levels = prog->d_levels;
+        A.big_nodes = prog->d_big_nodes;
+        A.big_ops = prog->d_big_ops;
+        A.big_inputs = prog->d_big_inputs;
+        A.consts = prog->d_consts;
+        A.n_limbs = n_limbs_dev + p0 * prog->num_limbs;
+        A.sig_limbs = sig_limbs_dev + p0 * prog->num_limbs;
+        A.hash_limbs = hash_limbs_dev + p0 * 4;
+        A.values = values;
+        A.is_valid = is_valid_dev + p0;
+        A.num_levels = prog->num_levels;
+        A.num_values = prog->num_values;
+        A.num_limbs = prog->num_limbs;
+        A.big_words = prog->max_big_words;
+        A.is_valid_vid = prog->is_valid_vid;
+        k_witness_eval<<<(unsigned)g, 1024, big_smem, ctx->stream>>>(A);
+        B2R_LAUNCH_CHECK(ctx);
+        dim3 grid((n + 255) / 256, NUM_ADVICE, (unsigned)g);
+        k_witness_emit<<<grid, 256, 0, ctx->stream>>>(prog->d_cellmap, values, prog->num_values, prog->k, n - BLINDING_ROWS, blind_seed,
+                                                      (uint32_t)(p_base + p0), (fe_t*)advice_dev + p0 * NUM_ADVICE * n);
+        B2R_LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
+int32_t b2r_rsa_witness_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
+                                  const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev,
+                                  uint8_t* is_valid_dev) {
+    return witness_run(ctx, prog, n_limbs_dev, sig_limbs_dev, hash_limbs_dev, batch, blind_seed, advice_dev, is_valid_dev, 0);
+}
+
+int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs, const uint64_t* sig_limbs,
+                              const uint64_t* hash_limbs, size_t batch, uint64_t blind_seed, b2r_fr* advice, uint8_t* is_valid) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!prog || !n_limbs || !sig_limbs || !hash_limbs || !advice || !is_valid) return fail(ctx, B2R_ERR_INVALID, "rsa_witness: null pointer");
+    if (batch == 0) return 0;
+    const size_t n = (size_t)1 << prog->k, nl = prog->num_limbs;
+    const size_t in_bytes = batch * (2 * nl + 4) * 8;
+    const size_t in_al = (in_bytes + 255) & ~(size_t)255;
+    // stage a bounded number of instances at a time (20 MiB of advice each at k = 17)
+    const size_t per_adv = NUM_ADVICE * n * sizeof(fe_t);
+    const size_t G = std::max<size_t>(1, std::min<size_t>(batch, ((size_t)4 << 30) / per_adv));
+    char* d = nullptr;
+    B2R_TRY(scratch_get(ctx, SC_STAGE, in_al + 256 + ((batch + 255) & ~(size_t)255) + G * per_adv, (void**)&d));
+    uint64_t* d_n = (uint64_t*)d;
+    uint64_t* d_s = d_n + batch * nl;
+    uint64_t* d_h = d_s + batch * nl;
+    uint8_t* d_valid = (uint8_t*)(d + in_al);
+    fe_t* d_adv = (fe_t*)(d + in_al + 256 + ((batch + 255) & ~(size_t)255));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_n, n_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_s, sig_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * 4 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t p0 = 0; p0 < batch; p0 += G) {
+        size_t g = std::min(G, batch - p0);
+        B2R_TRY(witness_run(ctx, prog, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * 4, g, blind_seed, (b2r_fr*)d_adv, d_valid + p0, p0));
+        B2R_CUDA(ctx, cudaMemcpyAsync((char*)advice + p0 * per_adv, d_adv, g * per_adv, cudaMemcpyDeviceToHost, ctx->stream));
+        B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    B2R_CUDA(ctx, cudaMemcpyAsync(is_valid, d_valid, batch, cudaMemcpyDeviceToHost, ctx->stream));
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"
