@@ -58,6 +58,13 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_msm_g1": [vp, vp, vp, sz, vp],
         "b2r_msm_g1_batch": [vp, vp, vp, sz, sz, vp],
         "b2r_msm_g1_batch_dev": [vp, vp, vp, sz, sz, vp],
+        "b2r_profile_enable": [vp, i32],
+        "b2r_profile_read": [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(C.c_double)],
+        "b2r_profile_dump": [vp, C.c_char_p, sz, i32],
+        "b2r_bases_download": [vp, vp, vp, sz],
+        "b2r_srs_setup": [vp, u32, vp, C.POINTER(vp), C.POINTER(vp)],
+        "b2r_rsa_commit_batch": [vp, vp, vp, vp, vp, vp, sz, u64, u32, u32, vp, vp, vp, vp],
+        "b2r_rsa_commit_batch_dev": [vp, vp, vp, vp, vp, vp, sz, u64, u32, u32, vp, vp, vp, vp],
         "b2r_rsa_program_build": [vp, u32, vp, sz, u32, C.POINTER(vp)],
         "b2r_prog_free": [vp, vp],
         "b2r_prog_info": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
@@ -68,6 +75,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the ABI symbol is missing: loud by design
         fn.argtypes = args
         fn.restype = i32
+    lib.b2r_prog_num_limbs.argtypes = [vp]
+    lib.b2r_prog_num_limbs.restype = i32
     lib.b2r_last_error.argtypes = [vp]
     lib.b2r_last_error.restype = C.c_char_p
     lib.b2r_version.argtypes = []
@@ -125,6 +134,20 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.b2r_launch_count(self.h))
+
+    def profile_enable(self, on: bool):
+        self._ck(self.lib.b2r_profile_enable(self.h, 1 if on else 0))
+
+    def profile_dump(self, clear: bool = True) -> dict:
+        """-> {kernel name: (total device ms, launches)} since the last clear"""
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.lib.b2r_profile_dump(self.h, buf, 1 << 16, 1 if clear else 0))
+        out = {}
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, ms, cnt = item.split(":")
+                out[name] = (float(ms), int(cnt))
+        return out
 
     def dev_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
@@ -207,6 +230,34 @@ class Context:
     def msm_batch_dev(self, bases: "Bases", scalars_dptr: int, m: int, n: int, out_dptr: int):
         self._ck(self.lib.b2r_msm_g1_batch_dev(self.h, bases.h, C.c_void_p(scalars_dptr), m, n, C.c_void_p(out_dptr)))
 
+    def srs_setup(self, k: int, secret: np.ndarray):
+        """ParamsKZG::setup(k) for a chosen secret (uint64[4] Montgomery) -> (g, g_lagrange)"""
+        secret = _fr_array(np.asarray(secret).reshape(4))
+        g, gl = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.b2r_srs_setup(self.h, k, _host_ptr(secret), C.byref(g), C.byref(gl)))
+        return Bases(self, g, 1 << k), Bases(self, gl, 1 << k)
+
+    def rsa_commit_batch(self, prog: "RsaProgram", g_lagrange: "Bases", n_limbs, sig_limbs, hash_limbs, ext_k: int,
+                         advice_dptr: int, ext_dptr: int, blind_seed: int = 0):
+        """fused hot path, HOST inputs -> (commitments uint64[batch,5,8], is_valid uint8[batch])"""
+        n_limbs = np.ascontiguousarray(n_limbs, dtype=np.uint64)
+        sig_limbs = np.ascontiguousarray(sig_limbs, dtype=np.uint64)
+        hash_limbs = np.ascontiguousarray(hash_limbs, dtype=np.uint64)
+        batch = n_limbs.shape[0]
+        cm = np.zeros((batch, 5, 8), dtype=np.uint64)
+        valid = np.zeros(batch, dtype=np.uint8)
+        self._ck(self.lib.b2r_rsa_commit_batch(self.h, prog.h, g_lagrange.h, _host_ptr(n_limbs), _host_ptr(sig_limbs),
+                                               _host_ptr(hash_limbs), batch, blind_seed, prog.k, ext_k,
+                                               C.c_void_p(advice_dptr), C.c_void_p(ext_dptr or 0), _host_ptr(cm), _host_ptr(valid)))
+        return cm, valid
+
+    def rsa_commit_batch_raw(self, prog, g_lagrange, n_ptr: int, s_ptr: int, h_ptr: int, batch: int, ext_k: int,
+                             advice_dptr: int, ext_dptr: int, cm_ptr: int, valid_ptr: int, blind_seed: int = 0, host: bool = False):
+        """same, raw pointers (pinned host buffers when host=True, device pointers otherwise); asynchronous for host=False"""
+        fn = self.lib.b2r_rsa_commit_batch if host else self.lib.b2r_rsa_commit_batch_dev
+        self._ck(fn(self.h, prog.h, g_lagrange.h, C.c_void_p(n_ptr), C.c_void_p(s_ptr), C.c_void_p(h_ptr), batch, blind_seed,
+                    prog.k, ext_k, C.c_void_p(advice_dptr), C.c_void_p(ext_dptr or 0), C.c_void_p(cm_ptr), C.c_void_p(valid_ptr)))
+
     # -- RSA witness (Circuit::synthesize of the pkcs1v15 circuit)
     def rsa_program(self, bits_len: int, k: int, e: int = 65537) -> "RsaProgram":
         e_le = np.frombuffer(e.to_bytes((e.bit_length() + 7) // 8, "little"), dtype=np.uint8).copy()
@@ -218,6 +269,12 @@ class Context:
 class Bases:
     def __init__(self, ctx: Context, h, n: int):
         self.ctx, self.h, self.n = ctx, h, n
+
+    def download(self, n: int | None = None) -> np.ndarray:
+        n = self.n if n is None else n
+        out = np.zeros((n, 8), dtype=np.uint64)
+        self.ctx._ck(self.ctx.lib.b2r_bases_download(self.ctx.h, self.h, _host_ptr(out), n))
+        return out
 
     def free(self):
         if self.h:

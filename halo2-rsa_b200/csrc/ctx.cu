@@ -86,6 +86,8 @@ int32_t b2r_ctx_destroy(b2r_ctx* ctx) {
     for (auto& kv : ctx->twiddles) cudaFree(kv.second);
     for (auto& s : ctx->scratch)
         if (s.p) cudaFree(s.p);
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+    for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -118,6 +120,62 @@ const char* b2r_last_error(const b2r_ctx* ctx) {
 }
 
 uint64_t b2r_launch_count(const b2r_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t b2r_profile_enable(b2r_ctx* ctx, int32_t on) {
+    if (!ctx) return B2R_ERR_INVALID;
+    ctx->profile = on != 0;
+    return 0;
+}
+
+// sums the recorded launches whose name matches `name` exactly; clears nothing
+int32_t b2r_profile_read(b2r_ctx* ctx, const char* name, double* total_ms, uint64_t* launches, double* units) {
+    if (!ctx || !name) return B2R_ERR_INVALID;
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0, u = 0;
+    uint64_t cnt = 0;
+    for (auto& r : ctx->prof) {
+        if (strcmp(r.name, name) != 0) continue;
+        float t = 0;
+        B2R_CUDA(ctx, cudaEventElapsedTime(&t, r.start, r.stop));
+        ms += t;
+        u += r.units;
+        cnt++;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = cnt;
+    if (units) *units = u;
+    return 0;
+}
+
+// writes "name:ms:launches;..." for every distinct name, then clears the records
+int32_t b2r_profile_dump(b2r_ctx* ctx, char* buf, size_t cap, int32_t clear) {
+    if (!ctx || !buf || cap == 0) return B2R_ERR_INVALID;
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::map<std::string, std::pair<double, uint64_t>> acc;
+    for (auto& r : ctx->prof) {
+        float t = 0;
+        B2R_CUDA(ctx, cudaEventElapsedTime(&t, r.start, r.stop));
+        auto& a = acc[r.name];
+        a.first += t;
+        a.second++;
+    }
+    std::string out;
+    for (auto& kv : acc) {
+        char tmp[160];
+        snprintf(tmp, sizeof tmp, "%s:%.6f:%llu;", kv.first.c_str(), kv.second.first, (unsigned long long)kv.second.second);
+        out += tmp;
+    }
+    if (out.size() + 1 > cap) return fail(ctx, B2R_ERR_INVALID, "profile_dump: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    if (clear) {
+        for (auto& r : ctx->prof) {
+            ctx->prof_pool.push_back(r.start);
+            ctx->prof_pool.push_back(r.stop);
+        }
+        ctx->prof.clear();
+    }
+    return 0;
+}
 
 int32_t b2r_dev_alloc(b2r_ctx* ctx, size_t bytes, void** dptr) {
     if (!ctx || !dptr) return B2R_ERR_INVALID;

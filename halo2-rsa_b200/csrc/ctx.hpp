@@ -23,6 +23,12 @@ struct TwiddleKey {
     }
 };
 
+struct ProfRec {
+    const char* name;
+    cudaEvent_t start, stop;
+    double units;  // caller-defined work units of this launch (e.g. MSM terms)
+};
+
 struct Scratch {
     void* p = nullptr;
     size_t cap = 0;
@@ -41,6 +47,10 @@ struct b2r_ctx {
     std::map<b2r::TwiddleKey, b2r::fe_t*> twiddles;
     // grow-only scratch arenas (ping-pong buffers, MSM work arrays, staging)
     b2r::Scratch scratch[8];
+    // optional per-kernel timing (b2r_profile_*): event pairs around selected launches
+    bool profile = false;
+    std::vector<b2r::ProfRec> prof;
+    std::vector<cudaEvent_t> prof_pool;
     void* pinned = nullptr;  // small pinned staging block
     size_t pinned_cap = 0;
 };
@@ -70,6 +80,31 @@ int32_t scratch_get(b2r_ctx* ctx, int slot, size_t bytes, void** out);
         cudaError_t _e = cudaGetLastError();                                   \
         if (_e != cudaSuccess) return b2r::cuda_fail(ctx, _e, "kernel launch"); \
     } while (0)
+
+// RAII scope that brackets kernel launches with events when profiling is on
+struct KTimer {
+    b2r_ctx* ctx;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    const char* name;
+    double units;
+    KTimer(b2r_ctx* c, const char* n, double u = 0) : ctx(c), name(n), units(u) {
+        if (!ctx->profile) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        start = get();
+        stop = get();
+        cudaEventRecord(start, ctx->stream);
+    }
+    ~KTimer() {
+        if (!start) return;
+        cudaEventRecord(stop, ctx->stream);
+        ctx->prof.push_back({name, start, stop, units});
+    }
+};
 
 // scratch arena slots
 enum { SC_NTT_PING = 0, SC_NTT_PONG = 1, SC_MSM_A = 2, SC_MSM_B = 3, SC_MSM_C = 4, SC_STAGE = 5, SC_WIT = 6, SC_MISC = 7 };

@@ -421,14 +421,18 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     B2R_CUDA(ctx, cudaMemsetAsync(cnt, 0, G * B * 4, st));
     B2R_CUDA(ctx, cudaMemsetAsync(bk, 0, G * B * sizeof(xyzz_t), st));
     dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
-    k_digits<false><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cnt, nullptr, 0);
+    { KTimer kt(ctx, "msm_count", (double)G * n);
+    k_digits<false><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cnt, nullptr, 0); }
     B2R_LAUNCH_CHECK(ctx);
-    k_scan<<<(unsigned)G, 1024, 0, st>>>(cnt, off, cur, B);
+    { KTimer kt(ctx, "msm_scan");
+    k_scan<<<(unsigned)G, 1024, 0, st>>>(cnt, off, cur, B); }
     B2R_LAUNCH_CHECK(ctx);
-    k_digits<true><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cur, ent, ent_cap);
+    { KTimer kt(ctx, "msm_scatter", (double)G * n);
+    k_digits<true><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cur, ent, ent_cap); }
     B2R_LAUNCH_CHECK(ctx);
+    { KTimer kt(ctx, "msm_accum_entries", (double)G * n);
     k_accum_entries<<<dim3((nch1 + 127) / 128, (unsigned)G), 128, 0, st>>>(bs->table, ent, ent_cap, off, B, L1, nch1, bk,
-                                                                          ka, pa, slotsA);
+                                                                          ka, pa, slotsA); }
     B2R_LAUNCH_CHECK(ctx);
     // upper levels: ping-pong slot lists until one chunk remains
     const uint32_t* ik = ka;
@@ -441,8 +445,9 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
         uint32_t* ok = to_b ? kb : ka;
         xyzz_t* op = to_b ? pb : pa;
         size_t out_stride = to_b ? slotsB : slotsA;
+        { KTimer kt(ctx, "msm_accum_slots");
         k_accum_slots<<<dim3((nch + 127) / 128, (unsigned)G), 128, 0, st>>>(ik, ip, in_stride, M, L2, nch, B, bk, ok, op,
-                                                                           out_stride);
+                                                                           out_stride); }
         B2R_LAUNCH_CHECK(ctx);
         if (nch == 1) break;
         ik = ok;
@@ -451,9 +456,11 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
         M = 2 * nch;
         to_b = !to_b;
     }
-    k_bucket_reduce<<<dim3(nblk, (unsigned)G), 256, 256 * sizeof(xyzz_t), st>>>(bk, B, per, blk, nblk);
+    { KTimer kt(ctx, "msm_bucket_reduce");
+    k_bucket_reduce<<<dim3(nblk, (unsigned)G), 256, 256 * sizeof(xyzz_t), st>>>(bk, B, per, blk, nblk); }
     B2R_LAUNCH_CHECK(ctx);
-    k_final<<<(unsigned)G, 32, 0, st>>>(blk, nblk, out_dev);
+    { KTimer kt(ctx, "msm_final");
+    k_final<<<(unsigned)G, 32, 0, st>>>(blk, nblk, out_dev); }
     B2R_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -466,6 +473,7 @@ static size_t msm_group_bytes(const b2r_bases* bs, size_t n) {
 }
 
 int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev) {
+    if (n > bs->n) return fail(ctx, B2R_ERR_INVALID, "msm: more scalars than registered bases");
     if (n == 0) {
         B2R_CUDA(ctx, cudaMemsetAsync(out_dev, 0, m * sizeof(affine_t), ctx->stream));
         return 0;
@@ -520,6 +528,14 @@ int32_t b2r_bases_register(b2r_ctx* ctx, const b2r_g1_affine* bases_host, size_t
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { cudaFree(bs->table); delete bs; return cuda_fail(ctx, e, "k_precompute"); }
     *out = bs;
+    return 0;
+}
+
+int32_t b2r_bases_download(b2r_ctx* ctx, const b2r_bases* bases, b2r_g1_affine* out_host, size_t n) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!bases || !out_host || n > bases->n) return fail(ctx, B2R_ERR_INVALID, "bases_download: bad argument");
+    B2R_CUDA(ctx, cudaMemcpyAsync(out_host, bases->table, n * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream));
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

@@ -309,7 +309,8 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         ntt_kernel_t kern = pass_kernel(S[p]);
         if (smem > 48 * 1024) B2R_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(1u << (log_cols - log_c), (unsigned)batch);
-        kern<<<grid, 256, smem, ctx->stream>>>(A);
+        { KTimer kt(ctx, "ntt_pass", (double)batch * n);
+        kern<<<grid, 256, smem, ctx->stream>>>(A); }
         B2R_LAUNCH_CHECK(ctx);
         if (last && dst != out) {
             B2R_CUDA(ctx, cudaMemcpy2DAsync(out, out_stride * 32, dst, dst_stride * 32, n * 32, batch, cudaMemcpyDeviceToDevice, ctx->stream));

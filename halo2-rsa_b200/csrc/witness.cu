@@ -553,6 +553,8 @@ int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog* prog) {
     return 0;
 }
 
+int32_t b2r_prog_num_limbs(const b2r_prog* prog) { return prog ? (int32_t)prog->num_limbs : B2R_ERR_INVALID; }
+
 int32_t b2r_prog_info(const b2r_prog* prog, uint64_t* rows_used, uint64_t* num_values, uint64_t* num_levels) {
     if (!prog) return B2R_ERR_INVALID;
     if (rows_used) *rows_used = prog->rows_used;
@@ -595,9 +597,11 @@ static int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n
         A.num_limbs = prog->num_limbs;
         A.big_words = prog->max_big_words;
         A.is_valid_vid = prog->is_valid_vid;
-        k_witness_eval<<<(unsigned)g, 1024, big_smem, ctx->stream>>>(A);
+        { KTimer kt(ctx, "witness_eval", (double)g);
+        k_witness_eval<<<(unsigned)g, 1024, big_smem, ctx->stream>>>(A); }
         B2R_LAUNCH_CHECK(ctx);
         dim3 grid((n + 255) / 256, NUM_ADVICE, (unsigned)g);
+        KTimer kt_emit(ctx, "witness_emit", (double)g);
         k_witness_emit<<<grid, 256, 0, ctx->stream>>>(prog->d_cellmap, values, prog->num_values, prog->k, n - BLINDING_ROWS, blind_seed,
                                                       (uint32_t)(p_base + p0), (fe_t*)advice_dev + p0 * NUM_ADVICE * n);
         B2R_LAUNCH_CHECK(ctx);

@@ -60,6 +60,14 @@ const char* b2r_version(void);
 /* number of kernel launches this context has enqueued so far (bench.py `gpu_launches`) */
 uint64_t b2r_launch_count(const b2r_ctx* ctx);
 
+/* optional per-kernel timing: when enabled, selected kernel launches are bracketed by CUDA
+ * events on the context's stream.  b2r_profile_read sums the launches recorded under one
+ * kernel name (total device ms, launch count, work units); b2r_profile_dump writes
+ * "name:ms:launches;" for all names and optionally clears the records. */
+int32_t b2r_profile_enable(b2r_ctx* ctx, int32_t on);
+int32_t b2r_profile_read(b2r_ctx* ctx, const char* name, double* total_ms, uint64_t* launches, double* units);
+int32_t b2r_profile_dump(b2r_ctx* ctx, char* buf, size_t cap, int32_t clear);
+
 /* plain device memory helpers so a host language needs no CUDA binding of its own */
 int32_t b2r_dev_alloc(b2r_ctx* ctx, size_t bytes, void** dptr);
 int32_t b2r_dev_free(b2r_ctx* ctx, void* dptr);
@@ -108,6 +116,13 @@ int32_t b2r_msm_g1_batch(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* sca
 int32_t b2r_msm_g1_batch_dev(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars_dev,
                              size_t m, size_t n, b2r_g1_affine* out_dev);
 
+/* copies the registered affine points (window 0 of the table) back to the host */
+int32_t b2r_bases_download(b2r_ctx* ctx, const b2r_bases* bases, b2r_g1_affine* out_host, size_t n);
+/* Replaces ParamsKZG::<Bn256>::setup(k, rng) (reference benches/bench.rs:235) for a caller-chosen
+ * secret: g[i] = s^i * G, g_lagrange[i] = L_i(s) * G over the 2^k domain; both sets are left
+ * resident and MSM-ready.  Either output may be NULL. */
+int32_t b2r_srs_setup(b2r_ctx* ctx, uint32_t k, const b2r_fr* secret, b2r_bases** g, b2r_bases** g_lagrange);
+
 /* ---- RSA witness synthesis ---------------------------------------------------------
  * Replaces the witness side of Circuit::synthesize for the reference's pkcs1v15 circuit
  * (benches/bench.rs:132-225, SHA-disabled branch) = RSAChip::verify_pkcs1v15_signature
@@ -120,6 +135,7 @@ int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog* prog);
 /* rows used by the layout (must be <= 2^k - blinding rows), number of recorded values */
 int32_t b2r_prog_info(const b2r_prog* prog, uint64_t* rows_used, uint64_t* num_values,
                       uint64_t* num_levels);
+int32_t b2r_prog_num_limbs(const b2r_prog* prog); /* bits_len / 64, < 0 on error */
 /* n_limbs, sig_limbs: batch x (bits_len/64) little-endian 64-bit limbs; hash_limbs:
  * batch x 4.  advice: batch x 5 x 2^k Fr, column-major per instance (HOST pointer);
  * is_valid: batch bytes (the value of the circuit's final is_valid cell).
@@ -132,6 +148,27 @@ int32_t b2r_rsa_witness_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const uint
                                   const uint64_t* sig_limbs_dev, const uint64_t* hash_limbs_dev,
                                   size_t batch, uint64_t blind_seed, b2r_fr* advice_dev,
                                   uint8_t* is_valid_dev);
+
+
+/* ---- fused hot path ---------------------------------------------------------------------
+ * What create_proof does with the advice columns of `batch` independent RSA instances
+ * (reference benches/bench.rs:321-329; SURVEY.md 3 Stack 1 steps 2 and 6), in one call with
+ * everything resident between the stages:
+ *   witness synthesis -> commit_lagrange(5 advice columns) -> lagrange_to_coeff -> coeff_to_extended.
+ * advice_dev: device buffer batch x 5 x 2^k Fr (holds coefficients on return when ext_dev is
+ * given, Lagrange values otherwise); ext_dev: device buffer batch x 5 x 2^ext_k Fr or NULL to
+ * stop after the commitments; commitments: batch x 5 affine points; is_valid: batch bytes
+ * (1 valid, 0 invalid, 0xFF = the reference's synthesize would have panicked).
+ * The non-_dev variant takes HOST inputs and returns HOST commitments / flags. */
+int32_t b2r_rsa_commit_batch(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g_lagrange,
+                             const uint64_t* n_limbs, const uint64_t* sig_limbs, const uint64_t* hash_limbs,
+                             size_t batch, uint64_t blind_seed, uint32_t k, uint32_t ext_k,
+                             b2r_fr* advice_dev, b2r_fr* ext_dev, b2r_g1_affine* commitments, uint8_t* is_valid);
+int32_t b2r_rsa_commit_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g_lagrange,
+                                 const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
+                                 const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed,
+                                 uint32_t k, uint32_t ext_k, b2r_fr* advice_dev, b2r_fr* ext_dev,
+                                 b2r_g1_affine* commitments_dev, uint8_t* is_valid_dev);
 
 #ifdef __cplusplus
 }
