@@ -16,6 +16,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <algorithm>
 #include <array>
 #include <map>
 #include <stdexcept>
@@ -835,6 +836,44 @@ class RSAChip {
         return is_eq;
     }
 };
+
+
+// ---- the bench circuit's synthesize (benches/bench.rs:132-225, sha2 disabled) ---------------------
+static constexpr uint32_t BLINDING_ROWS = 6;  // cs.blinding_factors() + 1 = 5 + 1 for this circuit
+
+// RangeChip::configure with RSAChip::compute_range_lens: distinct non-zero bit lengths, ascending tags
+inline void configure_range_tags(RegionCtx& rc, unsigned num_limbs) {
+    std::vector<unsigned> comp, over, lens;
+    RSAChip::compute_range_lens(num_limbs, comp, over);
+    for (unsigned v : comp) if (v) lens.push_back(v);
+    for (unsigned v : over) if (v) lens.push_back(v);
+    std::sort(lens.begin(), lens.end());
+    lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
+    for (size_t i = 0; i < lens.size(); i++) rc.tag_of_bits[lens[i]] = (int)i + 1;
+}
+
+// Records the whole circuit into `rc`; returns the is_valid cell.  Inputs are value nodes
+// OP_INPUT 0..nl-1 = n limbs, nl..2nl-1 = signature limbs, 2nl..2nl+3 = hash limbs.
+inline AssignedValue record_rsa_pkcs1v15(RegionCtx& rc, unsigned bits_len, const std::vector<uint8_t>& e_le) {
+    const unsigned nl = bits_len / 64;
+    configure_range_tags(rc, nl);
+    RSAChip rsa_chip(bits_len, 5);
+    BigIntChip bigint_chip = rsa_chip.bigint_chip();
+    MainGate main_gate;
+    UnassignedInteger sig_u, n_u, hash_u;
+    for (unsigned i = 0; i < nl; i++) n_u.limbs.push_back(rc.input(i));
+    for (unsigned i = 0; i < nl; i++) sig_u.limbs.push_back(rc.input(nl + i));
+    for (unsigned i = 0; i < 4; i++) hash_u.limbs.push_back(rc.input(2 * nl + i));
+    // region 1 (bench.rs:145-156): signature, then public key
+    AssignedRSASignature sign = rsa_chip.assign_signature(rc, sig_u);
+    AssignedRSAPublicKey public_key = rsa_chip.assign_public_key(rc, n_u, e_le);
+    // region 2 (bench.rs:186-211): hashed message, verification
+    AssignedInteger hashed = bigint_chip.assign_integer(rc, hash_u);
+    AssignedValue is_valid = rsa_chip.verify_pkcs1v15_signature(rc, public_key, hashed, sign);
+    // region 3 (bench.rs:213-221)
+    main_gate.assert_one(rc, is_valid);
+    return is_valid;
+}
 
 }  // namespace circuit
 }  // namespace b2r

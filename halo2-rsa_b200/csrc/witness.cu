@@ -483,7 +483,6 @@ static void prog_release(b2r_prog* p) {
     delete p;
 }
 
-static constexpr uint32_t BLINDING_ROWS = 6;  // cs.blinding_factors() + 1 = 5 + 1 for this circuit
 
 extern "C" {
 
@@ -502,34 +501,9 @@ int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_
     prog->k = k;
     prog->num_inputs = 2 * prog->num_limbs + 4;
     try {
-        const uint32_t nl = prog->num_limbs;
         RegionCtx rc((1u << k) - BLINDING_ROWS);
-        // RangeChip::configure with RSAChip::compute_range_lens: distinct non-zero bit lengths, ascending tags
-        std::vector<unsigned> comp, over;
-        RSAChip::compute_range_lens(nl, comp, over);
-        std::vector<unsigned> lens;
-        for (unsigned v : comp) if (v) lens.push_back(v);
-        for (unsigned v : over) if (v) lens.push_back(v);
-        std::sort(lens.begin(), lens.end());
-        lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
-        for (size_t i = 0; i < lens.size(); i++) rc.tag_of_bits[lens[i]] = (int)i + 1;
-
-        RSAChip rsa_chip(bits_len, 5);
-        BigIntChip bigint_chip = rsa_chip.bigint_chip();
-        MainGate main_gate;
         std::vector<uint8_t> e(e_le, e_le + e_len);
-        // region 1 (bench.rs:145-156): signature, then public key
-        UnassignedInteger sig_u, n_u, hash_u;
-        for (uint32_t i = 0; i < nl; i++) n_u.limbs.push_back(rc.input(i));
-        for (uint32_t i = 0; i < nl; i++) sig_u.limbs.push_back(rc.input(nl + i));
-        for (uint32_t i = 0; i < 4; i++) hash_u.limbs.push_back(rc.input(2 * nl + i));
-        AssignedRSASignature sign = rsa_chip.assign_signature(rc, sig_u);
-        AssignedRSAPublicKey public_key = rsa_chip.assign_public_key(rc, n_u, e);
-        // region 2 (bench.rs:186-211): hashed message, verification
-        AssignedInteger hashed = bigint_chip.assign_integer(rc, hash_u);
-        AssignedValue is_valid = rsa_chip.verify_pkcs1v15_signature(rc, public_key, hashed, sign);
-        // region 3 (bench.rs:213-221)
-        main_gate.assert_one(rc, is_valid);
+        AssignedValue is_valid = record_rsa_pkcs1v15(rc, bits_len, e);
         int32_t r = finalize_program(ctx, rc, is_valid, prog);
         if (r) {
             prog_release(prog);

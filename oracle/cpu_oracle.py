@@ -154,3 +154,28 @@ def rsa_synthesize(bits_len: int, k: int, n: int, sig: int, hashed: int, e: int 
     out = (v, t.advice(), t.rows(), bad, msg)
     t.free()
     return out
+
+
+# ---- single BigIntChip operations (the reference's impl_bigint_test_circuit! bodies) ------------
+BIGINT_OPS = {"mul_kat": 0, "mul_mod": 1, "pow_mod_fixed_exp": 2, "add": 3, "sub": 4, "assert_in_field": 5}
+
+
+def bigint_op(op: str, bits_len: int, k: int, a: int, b: int = 0, n: int = 0):
+    """runs one BigIntChip operation in a fresh table, the way the reference's unit-test circuits do
+    (src/big_integer/chip.rs:1470-3264).  -> (result limbs as ints or None if the reference would have
+    panicked, number of violated constraints reported by the MockProver-style checker)"""
+    nl = bits_len // 64
+    t = RsaTable(bits_len, k)
+    nw = 2 * nl if op == "mul_kat" else nl
+    aw, bw = int_to_limbs64(a, nl), int_to_limbs64(b, nl)
+    nwords = int_to_limbs64(n, nw)
+    out = np.zeros((2 * nl + 2, 4), dtype=np.uint64)
+    L = lib()
+    L.orc_bigint_op.restype = C.c_int
+    r = L.orc_bigint_op(t.h, C.c_int(BIGINT_OPS[op]), C.c_int(bits_len), _p(aw), _p(bw), _p(nwords), C.c_int(nw), _p(out))
+    bad, _ = t.check()
+    t.free()
+    if r < 0:
+        return None, bad
+    limbs = [int(out[i, 0]) | (int(out[i, 1]) << 64) | (int(out[i, 2]) << 128) | (int(out[i, 3]) << 192) for i in range(r)]
+    return limbs, bad

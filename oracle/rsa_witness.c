@@ -619,6 +619,84 @@ int orc_rsa_synthesize(orc_table* t, int bits_len, const uint8_t* e_le, int e_le
     return fe_eq(&is_valid.v, &FR.one) ? 1 : 0;
 }
 
+/* ---- single BigIntChip operations, as the reference's in-file test circuits drive them -------------
+ * (src/big_integer/chip.rs:1470-3264: impl_bigint_test_circuit! bodies).  Integers come in as
+ * little-endian 64-bit words.  out receives the result limbs as canonical 4 x u64 each.
+ *   op 0  test_mul_case*:     a,b = assign_constant_fresh; ab = mul(a,b); ans = assign_constant_muled(n);
+ *                              assert_equal_muled(ab, ans)               out = 2*nl-1 unreduced limbs of ab
+ *   op 1  test_mulmod_case*:   a,b,n = assign_integer; r = mul_mod(a,b,n)  out = nl limbs of r
+ *   op 2  test_pow_mod_fixed_exp: a,n = assign_integer; r = pow_mod_fixed_exp(a, e=b_words[0], n)
+ *   op 3  test_add:            c = add(a,b)                               out = nl+1 limbs
+ *   op 4  test_sub:            (c, overflow) = sub(a,b)                   out = nl limbs, then overflow bit
+ *   op 5  test_assert_in_field: assert_in_field(a, n)
+ * returns the number of out limbs, or -1 when the reference would have panicked. */
+static void words_to_big(const uint64_t* w, int nwords, big* out) {
+    out->n = 2 * nwords;
+    for (int i = 0; i < nwords; i++) { out->w[2 * i] = (uint32_t)w[i]; out->w[2 * i + 1] = (uint32_t)(w[i] >> 32); }
+    big_norm(out);
+}
+int orc_bigint_op(orc_table* t, int op, int bits_len, const uint64_t* a_words, const uint64_t* b_words,
+                  const uint64_t* n_words, int n_words_len, uint64_t* out) {
+    rctx* c = &t->c;
+    int nl = bits_len / 64;
+    bigchip ch = {64, nl};
+    fe tmp[MAXL];
+    bint a, b, n, r;
+    int nout = 0;
+    if (op == 0) {
+        big ab_, bb_, nb_;
+        words_to_big(a_words, nl, &ab_); words_to_big(b_words, nl, &bb_); words_to_big(n_words, n_words_len, &nb_);
+        bi_assign_constant(c, &ch, &ab_, nl, &a);
+        bi_assign_constant(c, &ch, &bb_, nl, &b);
+        bi_mul(c, &a, &b, &r);
+        bint ans; bi_assign_constant(c, &ch, &nb_, 2 * nl - 1, &ans);
+        aval eq; bi_is_equal_muled(c, &ch, &r, &ans, nl, nl, &eq);
+        mg_assert_one(c, &eq);
+        nout = r.n;
+    } else {
+        for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(a_words[i]);
+        bi_assign_integer(c, &ch, tmp, nl, &a);
+        if (op != 2) { for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(b_words[i]); bi_assign_integer(c, &ch, tmp, nl, &b); }
+        if (op == 1 || op == 2 || op == 5) { for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(n_words[i]); bi_assign_integer(c, &ch, tmp, nl, &n); }
+        if (op == 1) { bi_mul_mod(c, &ch, &a, &b, &n, &r); nout = r.n; }
+        else if (op == 2) {
+            uint8_t e_le[8]; for (int i = 0; i < 8; i++) e_le[i] = (uint8_t)(b_words[0] >> (8 * i));
+            bi_pow_mod_fixed_exp(c, &ch, &a, e_le, 8, &n, &r); nout = r.n;
+        } else if (op == 3) { bi_add(c, &ch, &a, &b, &r); nout = r.n; }
+        else if (op == 4) { aval ov; bi_sub(c, &ch, &a, &b, &r, &ov); r.l[r.n] = ov; nout = r.n + 1; }
+        else if (op == 5) { bi_assert_in_field(c, &ch, &a, &n); nout = 0; }
+        else return -2;
+    }
+    for (int i = 0; i < nout; i++) fe_canon(&r.l[i].v, out + 4 * i);
+    return c->failed ? -1 : nout;
+}
+
+/* layout digest, compared with the product's host-side circuit recorder (tests/test_host_circuit.py):
+ * out[0] = rows used, out[1] = order-independent hash of all fixed cells (canonical values),
+ * out[2] = number of copy constraints, out[3] = order-independent hash of the copy constraints,
+ * out[4] = hash of the range selectors / tags */
+static uint64_t mix64(uint64_t h, uint64_t v) { h ^= v; h *= 0x100000001B3ull; h ^= h >> 29; return h; }
+void orc_table_layout_digest(const orc_table* t, uint64_t* out) {
+    const rctx* c = &t->c;
+    uint64_t hf = 0, hc = 0, hr = 0;
+    for (size_t r = 0; r < c->offset && r < c->nrows; r++) {
+        for (int f = 0; f < NFIX; f++) {
+            uint64_t v[4]; fe_canon(&c->fix[f][r], v);
+            if (!(v[0] | v[1] | v[2] | v[3])) continue;
+            uint64_t h = mix64(mix64(0xcbf29ce484222325ull, r), f);
+            for (int i = 0; i < 4; i++) h = mix64(h, v[i]);
+            hf += h;
+        }
+        uint64_t h = mix64(mix64(mix64(mix64(mix64(0xcbf29ce484222325ull, r), c->s_comp[r]), c->tag_comp[r]), c->s_over[r]), c->tag_over[r]);
+        if (c->s_comp[r] | c->s_over[r]) hr += h;
+    }
+    for (size_t i = 0; i < c->ncopies; i++) {
+        const uint32_t* e = c->copies[i];
+        hc += mix64(mix64(mix64(mix64(0xcbf29ce484222325ull, e[0]), e[1]), e[2]), e[3]);
+    }
+    out[0] = c->offset; out[1] = hf; out[2] = c->ncopies; out[3] = hc; out[4] = hr;
+}
+
 /* ---- MockProver-style check ----------------------------------------------------------------------------- */
 /* returns the number of violated constraints (0 = satisfied); first few are described in msg */
 long orc_check(const orc_table* t, char* msg, size_t msg_cap) {

@@ -1,0 +1,78 @@
+"""CPU: host logic of the product - the circuit recorder (csrc/circuit.hpp), i.e. the host-side
+mirror of RSAChip / BigIntChip / maingate that produces the GPU witness program - compiled by g++
+and compared with the oracle's independently written row-by-row synthesis: same rows, same fixed
+columns, same copy constraints, same range-lookup tags, for every BASELINE key size."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cpu_oracle as CO
+import rsa_fixtures as RF
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("host") / "circuit_host_test")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", out, os.path.join(HERE, "host", "circuit_host_test.cpp")])
+    return out
+
+
+def record(exe, bits, k, e=65537):
+    p = subprocess.run([exe, str(bits), str(k), str(e)], capture_output=True, text=True)
+    return p.returncode, dict(re.findall(r"(\w+)=(\S+)", p.stdout)), p.stdout
+
+
+def oracle_digest(bits, k, e=65537):
+    t = CO.RsaTable(bits, k)
+    n, s, h = RF.instance(bits, 0)
+    nl = bits // 64
+    assert t.synthesize(RF.limbs64(n, nl), RF.limbs64(s, nl), RF.limbs64(h, 4), e) >= 0
+    out = np.zeros(5, dtype=np.uint64)
+    CO.lib().orc_table_layout_digest(t.h, C.c_void_p(out.ctypes.data))
+    t.free()
+    return [int(x) for x in out]
+
+
+@pytest.mark.parametrize("bits,k", [(1024, 15), (2048, 17), (4096, 18)])
+def test_recorded_layout_equals_oracle_layout(exe, bits, k):
+    rc, d, raw = record(exe, bits, k)
+    assert rc == 0, raw
+    rows, hf, ncop, hc, hr = oracle_digest(bits, k)
+    assert int(d["rows"]) == rows
+    assert int(d["fixed"]) == hf
+    assert int(d["ncopies"]) == ncop and int(d["copies"]) == hc
+    assert int(d["range"]) == hr
+    nl = bits // 64
+    assert int(d["bigops"]) == 19 + 2          # 17 squarings + 2 multiplications, 2 sub_unchecked (assert_in_field)
+    assert int(d["nodes"]) > 19 * 2 * nl * nl  # at least the mul_add chains
+
+
+def test_layout_is_data_independent():
+    """the call sequence does not depend on the witness -> same digest for other inputs"""
+    t = CO.RsaTable(2048, 17)
+    digs = []
+    for i in (0, 5):
+        t = CO.RsaTable(2048, 17)
+        n, s, h = RF.instance(2048, i)
+        t.synthesize(RF.limbs64(n, 32), RF.limbs64(s, 32), RF.limbs64(h, 4))
+        out = np.zeros(5, dtype=np.uint64)
+        CO.lib().orc_table_layout_digest(t.h, C.c_void_p(out.ctypes.data))
+        digs.append(out.tolist())
+        t.free()
+    assert digs[0] == digs[1]
+
+
+def test_other_exponents_and_errors(exe):
+    rc, d, _ = record(exe, 1024, 15, e=3)
+    assert rc == 0 and int(d["bigops"]) == 2 + 2 + 2      # 2 squarings + 2 multiplications + in-field subs
+    assert int(d["rows"]) == oracle_digest(1024, 15, e=3)[0]
+    rc, d, raw = record(exe, 2048, 16)                   # does not fit 2^16 rows -> B2R_ERR_LAYOUT
+    assert rc == 2 and "error=-5" in raw
+    rc, d, raw = record(exe, 2000, 17)                   # bits_len % limb_width != 0 (chip.rs:1175 assert)
+    assert rc == 2 and "error=-1" in raw
