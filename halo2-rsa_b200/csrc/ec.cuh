@@ -136,6 +136,96 @@ B2R_HD void xyzz_add(xyzz_t& acc, const xyzz_t& q) {
     acc.zzz = Fq::mul(Fq::mul(acc.zzz, q.zzz), PPP);
 }
 
+// ---- lock-step variants -----------------------------------------------------------------------
+// Same results as xyzz_madd / xyzz_add, written so that all lanes of a warp execute the same
+// instruction stream: the general formulas run unconditionally and the identity cases are
+// resolved with selects; only the P + P / P - P case (equal x) branches, and it is rare.
+B2R_HD fe_t fe_select(bool c, const fe_t& a, const fe_t& b) {
+    fe_t r;
+    for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+B2R_HD xyzz_t xyzz_from_affine_signed(const affine_t& p, bool neg) {
+    bool id = affine_is_identity(p);
+    xyzz_t r;
+    r.x = p.x;
+    r.y = neg ? Fq::neg(p.y) : p.y;
+    r.zz = id ? Fq::zero() : Fq::one();
+    r.zzz = r.zz;
+    return r;
+}
+B2R_HD void xyzz_madd_ls(xyzz_t& acc, const affine_t& q, bool neg) {
+    const bool q_id = affine_is_identity(q), a_id = xyzz_is_identity(acc);
+    fe_t qy = neg ? Fq::neg(q.y) : q.y;
+    fe_t U2 = Fq::mul(q.x, acc.zz);
+    fe_t S2 = Fq::mul(qy, acc.zzz);
+    fe_t P = Fq::sub(U2, acc.x);
+    fe_t R = Fq::sub(S2, acc.y);
+    if (!q_id && !a_id && Fq::is_zero(P)) {
+        if (Fq::is_zero(R)) {
+            affine_t t;
+            t.x = q.x;
+            t.y = qy;
+            acc = xyzz_double_affine(t);
+        } else {
+            acc = xyzz_identity();
+        }
+        return;
+    }
+    fe_t PP = Fq::sqr(P);
+    fe_t PPP = Fq::mul(P, PP);
+    fe_t Q = Fq::mul(acc.x, PP);
+    fe_t X3 = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
+    fe_t Y3 = Fq::sub(Fq::mul(R, Fq::sub(Q, X3)), Fq::mul(acc.y, PPP));
+    fe_t ZZ3 = Fq::mul(acc.zz, PP);
+    fe_t ZZZ3 = Fq::mul(acc.zzz, PPP);
+    if (a_id) {
+        X3 = q.x;
+        Y3 = qy;
+        ZZ3 = Fq::one();
+        ZZZ3 = Fq::one();
+    }
+    if (!q_id) {
+        acc.x = X3;
+        acc.y = Y3;
+        acc.zz = ZZ3;
+        acc.zzz = ZZZ3;
+    }
+}
+B2R_HD void xyzz_add_ls(xyzz_t& acc, const xyzz_t& q) {
+    const bool q_id = xyzz_is_identity(q), a_id = xyzz_is_identity(acc);
+    fe_t U1 = Fq::mul(acc.x, q.zz);
+    fe_t U2 = Fq::mul(q.x, acc.zz);
+    fe_t S1 = Fq::mul(acc.y, q.zzz);
+    fe_t S2 = Fq::mul(q.y, acc.zzz);
+    fe_t P = Fq::sub(U2, U1);
+    fe_t R = Fq::sub(S2, S1);
+    if (!q_id && !a_id && Fq::is_zero(P)) {
+        if (Fq::is_zero(R)) acc = xyzz_double(acc);
+        else acc = xyzz_identity();
+        return;
+    }
+    fe_t PP = Fq::sqr(P);
+    fe_t PPP = Fq::mul(P, PP);
+    fe_t Q = Fq::mul(U1, PP);
+    fe_t X3 = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
+    fe_t Y3 = Fq::sub(Fq::mul(R, Fq::sub(Q, X3)), Fq::mul(S1, PPP));
+    fe_t ZZ3 = Fq::mul(Fq::mul(acc.zz, q.zz), PP);
+    fe_t ZZZ3 = Fq::mul(Fq::mul(acc.zzz, q.zzz), PPP);
+    if (a_id) {
+        X3 = q.x;
+        Y3 = q.y;
+        ZZ3 = q.zz;
+        ZZZ3 = q.zzz;
+    }
+    if (!q_id) {
+        acc.x = X3;
+        acc.y = Y3;
+        acc.zz = ZZ3;
+        acc.zzz = ZZZ3;
+    }
+}
+
 // normalise; identity -> (0, 0)
 B2R_HD affine_t xyzz_to_affine(const xyzz_t& p) {
     affine_t r;

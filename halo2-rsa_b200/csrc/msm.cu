@@ -139,7 +139,7 @@ struct DigitIter {
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
 k_digits(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_t c, uint32_t W, uint32_t B,
-         uint32_t* counts /*[G][B] (count) or cursor (scatter)*/, uint32_t* entries, size_t ent_stride) {
+         uint32_t* counts /*[G][B] (count) or cursor (scatter)*/, uint32_t* entries, uint32_t* keys, size_t ent_stride) {
     uint32_t g = blockIdx.y;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
@@ -149,6 +149,7 @@ k_digits(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_
     it.init(s);
     uint32_t* cnt = counts + (size_t)g * B;
     uint32_t* ent = SCATTER ? entries + (size_t)g * ent_stride : nullptr;
+    uint32_t* key = SCATTER ? keys + (size_t)g * ent_stride : nullptr;
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t j = 0; j < W; j++) {
         int32_t d = it.next(j, c);
@@ -165,6 +166,7 @@ k_digits(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_
             if (SCATTER) {
                 base = __shfl_sync(peers, base, leader);
                 ent[base + rank] = (j * n_table + i) | (d < 0 ? 0x80000000u : 0u);
+                key[base + rank] = b;
             }
         }
     }
@@ -224,63 +226,71 @@ __device__ __forceinline__ void emit_run(uint32_t b, const xyzz_t& acc, bool beg
     }
 }
 
-__global__ void __launch_bounds__(128)
-k_accum_entries(const affine_t* __restrict__ table, const uint32_t* __restrict__ entries, size_t ent_stride,
-                const uint32_t* __restrict__ offsets, uint32_t B, uint32_t L, uint32_t nchunks, xyzz_t* buckets,
+// Lock-step formulation: every thread owns exactly L consecutive entries of the bucket-sorted list
+// and walks them with ONE flat loop, so all lanes of a warp execute the same mixed add in the same
+// iteration whatever the bucket boundaries are (the nested run loops of the first version left 9.8
+// of 32 lanes active, profiles/r01_ncu_full_baseline.md).  A bucket change costs a predicated flush.
+template <int L>
+__global__ void __launch_bounds__(128, 4)
+k_accum_entries(const affine_t* __restrict__ table, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ keys,
+                size_t ent_stride, const uint32_t* __restrict__ offsets, uint32_t B, uint32_t nchunks, xyzz_t* buckets,
                 uint32_t* slot_keys, xyzz_t* slot_pts, size_t slot_stride) {
     uint32_t g = blockIdx.y;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nchunks) return;
     const uint32_t* off = offsets + (size_t)g * (B + 1);
     const uint32_t* ent = entries + (size_t)g * ent_stride;
+    const uint32_t* key = keys + (size_t)g * ent_stride;
     xyzz_t* bk = buckets + (size_t)g * B;
     uint32_t* sk = slot_keys + (size_t)g * slot_stride;
     xyzz_t* sp = slot_pts + (size_t)g * slot_stride;
     size_t slot0 = 2 * (size_t)t;
     sk[slot0] = SLOT_INVALID;
     sk[slot0 + 1] = SLOT_INVALID;
-    uint32_t E = off[B];
-    uint32_t start = t * L;
+    const uint32_t E = off[B];
+    const uint32_t start = t * L;
     if (start >= E) return;
-    uint32_t end = min(start + L, E);
-    // bucket containing `start`: largest b with off[b] <= start
-    uint32_t lo = 0, hi = B;  // invariant off[lo] <= start < off[hi]
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (off[mid] <= start) lo = mid; else hi = mid;
+    const uint32_t end = min(start + (uint32_t)L, E);
+    uint32_t cur = key[start];
+    bool begins = (off[cur] == start), first = true;
+    uint32_t e = ent[start];
+    xyzz_t acc = xyzz_from_affine_signed(ldg_affine(table + (e & 0x7fffffffu)), (e >> 31) != 0);
+    uint32_t e_next = 0, k_next = cur;
+    affine_t p_next;
+    p_next.x = Fq::zero();
+    p_next.y = Fq::zero();
+    if (start + 1 < end) {
+        e_next = ent[start + 1];
+        k_next = key[start + 1];
+        p_next = ldg_affine(table + (e_next & 0x7fffffffu));
     }
-    uint32_t b = lo;
-    uint32_t pos = start;
-    bool first = true;
-    uint32_t e_next = ent[pos];
-    affine_t p_next = ldg_affine(table + (e_next & 0x7fffffffu));
-    while (pos < end) {
-        uint32_t bucket_end = off[b + 1];
-        while (bucket_end <= pos) {
-            b++;
-            bucket_end = off[b + 1];
+#pragma unroll 1
+    for (uint32_t pos = start + 1; pos < end; pos++) {
+        const uint32_t ec = e_next, kc = k_next;
+        const affine_t p = p_next;
+        if (pos + 1 < end) {
+            e_next = ent[pos + 1];
+            k_next = key[pos + 1];
+            p_next = ldg_affine(table + (e_next & 0x7fffffffu));
         }
-        uint32_t run_end = min(bucket_end, end);
-        bool begins = (pos == off[b]), ends = (run_end == bucket_end);
-        xyzz_t acc = xyzz_identity();
-        for (; pos < run_end; pos++) {
-            uint32_t e = e_next;
-            affine_t p = p_next;
-            if (pos + 1 < end) {
-                e_next = ent[pos + 1];
-                p_next = ldg_affine(table + (e_next & 0x7fffffffu));
-            }
-            xyzz_madd(acc, p, (e >> 31) != 0);
+        if (kc != cur) {
+            emit_run(cur, acc, begins, true, first, bk, sk, sp, slot0);
+            first = false;
+            begins = true;
+            cur = kc;
+            acc = xyzz_from_affine_signed(p, (ec >> 31) != 0);
+        } else {
+            xyzz_madd_ls(acc, p, (ec >> 31) != 0);
         }
-        emit_run(b, acc, begins, ends, first, bk, sk, sp, slot0);
-        first = false;
     }
+    emit_run(cur, acc, begins, end == off[cur + 1], first, bk, sk, sp, slot0);
 }
 
+// upper levels: the same walk over a slot list (key + XYZZ partial sum per slot)
+template <int L>
 __global__ void __launch_bounds__(128)
 k_accum_slots(const uint32_t* __restrict__ in_keys, const xyzz_t* __restrict__ in_pts, size_t in_stride, uint32_t M,
-              uint32_t L, uint32_t nchunks, uint32_t B, xyzz_t* buckets, uint32_t* slot_keys, xyzz_t* slot_pts,
-              size_t slot_stride) {
+              uint32_t nchunks, uint32_t B, xyzz_t* buckets, uint32_t* slot_keys, xyzz_t* slot_pts, size_t slot_stride) {
     uint32_t g = blockIdx.y;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nchunks) return;
@@ -292,17 +302,18 @@ k_accum_slots(const uint32_t* __restrict__ in_keys, const xyzz_t* __restrict__ i
     size_t slot0 = 2 * (size_t)t;
     sk[slot0] = SLOT_INVALID;
     sk[slot0 + 1] = SLOT_INVALID;
-    uint32_t start = t * L, end = min(start + L, M);
+    const uint32_t start = t * L, end = min(start + (uint32_t)L, M);
     bool have = false, first = true, begins = false, ends = false;
     uint32_t cb = 0;
     xyzz_t acc = xyzz_identity();
+#pragma unroll 1
     for (uint32_t s = start; s < end; s++) {
-        uint32_t key = ik[s];
+        const uint32_t key = ik[s];
         if (key == SLOT_INVALID) continue;
-        uint32_t b = key & SLOT_KEY;
+        const uint32_t b = key & SLOT_KEY;
+        const xyzz_t q = ld_xyzz(ip + s);
         if (have && b == cb) {
-            xyzz_t q = ld_xyzz(ip + s);
-            xyzz_add(acc, q);
+            xyzz_add_ls(acc, q);
             ends = (key & SLOT_ENDS) != 0;
         } else {
             if (have) {
@@ -311,7 +322,7 @@ k_accum_slots(const uint32_t* __restrict__ in_keys, const xyzz_t* __restrict__ i
             }
             have = true;
             cb = b;
-            acc = ld_xyzz(ip + s);
+            acc = q;
             begins = (key & SLOT_BEGINS) != 0;
             ends = (key & SLOT_ENDS) != 0;
         }
@@ -320,40 +331,77 @@ k_accum_slots(const uint32_t* __restrict__ in_keys, const xyzz_t* __restrict__ i
 }
 
 // ---- sum_b (b+1) * B_b -------------------------------------------------------------------
-// block = 256 threads x `per` consecutive buckets each
-__global__ void __launch_bounds__(256)
-k_bucket_reduce(const xyzz_t* __restrict__ buckets, uint32_t B, uint32_t per, xyzz_t* block_out, uint32_t nblk) {
-    extern __shared__ uint4 smem_raw[];
+// CTA = 128 threads x `per` consecutive buckets.  Thread t: S_t = sum of its buckets and
+// A_t = sum (d+1) * B_{lo+d} by running sums (2 adds per bucket).  The CTA then needs
+// sum_t (A_t + t*per*S_t) + base * sum_t S_t:  sum_t t*S_t = sum_{j>=1} (suffix sum T_j) comes from a
+// shared-memory suffix scan (7 steps), so no thread multiplies by its own offset.
+static constexpr int BR_THREADS = 128;
+__global__ void __launch_bounds__(BR_THREADS, 3)
+k_bucket_reduce(const xyzz_t* __restrict__ buckets, uint32_t B, uint32_t per, uint32_t log_per, xyzz_t* block_out, uint32_t nblk) {
+    __shared__ uint4 smem_raw[BR_THREADS * sizeof(xyzz_t) / sizeof(uint4)];
     xyzz_t* sm = reinterpret_cast<xyzz_t*>(smem_raw);
-    uint32_t g = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+    const uint32_t g = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
     const xyzz_t* bk = buckets + (size_t)g * B;
-    uint32_t lo = (blk * 256 + tid) * per;
+    const uint32_t base = blk * BR_THREADS * per, lo = base + tid * per;
     xyzz_t run = xyzz_identity(), acc = xyzz_identity();
+#pragma unroll 1
     for (uint32_t d = per; d-- > 0;) {
         xyzz_t q = ld_xyzz(bk + lo + d);
-        xyzz_add(run, q);
-        xyzz_add(acc, run);
+        // sparse bucket sets (small scalars): skip the adds a whole warp does not need
+        if (!__all_sync(0xffffffffu, xyzz_is_identity(q))) xyzz_add_ls(run, q);
+        if (!__all_sync(0xffffffffu, xyzz_is_identity(run))) xyzz_add_ls(acc, run);
     }
-    // acc = sum (b - lo + 1) B_b ; add lo * run
-    if (lo != 0 && !xyzz_is_identity(run)) {
-        xyzz_t tmp = xyzz_identity();
-        for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
-            tmp = xyzz_double(tmp);
-            if ((lo >> bit) & 1u) xyzz_add(tmp, run);
-        }
-        xyzz_add(acc, tmp);
-    }
-    sm[tid] = acc;
+    // inclusive suffix scan of S_t (Hillis-Steele)
+    sm[tid] = run;
     __syncthreads();
-    for (uint32_t s = 128; s > 0; s >>= 1) {
+#pragma unroll 1
+    for (uint32_t d = 1; d < BR_THREADS; d <<= 1) {
+        xyzz_t o = xyzz_identity();
+        if (tid + d < BR_THREADS) o = sm[tid + d];
+        __syncthreads();
+        xyzz_add_ls(run, o);
+        sm[tid] = run;
+        __syncthreads();
+    }
+    // run = T_tid.  tree-sum of T_t (t >= 1), then of A_t
+    xyzz_t total_s = sm[0];
+    __syncthreads();
+    if (tid == 0) sm[0] = xyzz_identity();
+    __syncthreads();
+    for (uint32_t s = BR_THREADS / 2; s > 0; s >>= 1) {
         if (tid < s) {
             xyzz_t a = sm[tid], b = sm[tid + s];
-            xyzz_add(a, b);
+            xyzz_add_ls(a, b);
             sm[tid] = a;
         }
         __syncthreads();
     }
-    if (tid == 0) st_xyzz(block_out + (size_t)g * nblk + blk, sm[0]);
+    xyzz_t w = sm[0];  // sum_t t * S_t
+    __syncthreads();
+    sm[tid] = acc;
+    __syncthreads();
+    for (uint32_t s = BR_THREADS / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            xyzz_t a = sm[tid], b = sm[tid + s];
+            xyzz_add_ls(a, b);
+            sm[tid] = a;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        xyzz_t r = sm[0];
+        for (uint32_t i = 0; i < log_per; i++) w = xyzz_double(w);  // per * sum t S_t
+        xyzz_add(r, w);
+        if (base != 0 && !xyzz_is_identity(total_s)) {
+            xyzz_t tmp = xyzz_identity();
+            for (int bit = 31 - __clz(base); bit >= 0; bit--) {
+                tmp = xyzz_double(tmp);
+                if ((base >> bit) & 1u) xyzz_add(tmp, total_s);
+            }
+            xyzz_add(r, tmp);
+        }
+        st_xyzz(block_out + (size_t)g * nblk + blk, r);
+    }
 }
 
 __global__ void __launch_bounds__(32) k_final(const xyzz_t* __restrict__ block_out, uint32_t nblk, affine_t* out) {
@@ -386,20 +434,23 @@ static uint32_t pick_window(size_t n) {
 
 static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t G, size_t n, affine_t* out_dev) {
     const uint32_t c = bs->c, W = bs->W, B = 1u << (c - 1);
-    const uint32_t L1 = 32, L2 = 16;
+    constexpr uint32_t L1 = 32, L2 = 16;
     const size_t ent_cap = (size_t)n * W;
     const uint32_t nch1 = (uint32_t)((ent_cap + L1 - 1) / L1);
     const size_t slotsA = 2 * (size_t)nch1;
     const uint32_t nch2 = (uint32_t)((slotsA + L2 - 1) / L2);
     const size_t slotsB = 2 * (size_t)nch2;
-    uint32_t per = B >= 4096 ? 16 : B / 256;
-    uint32_t nblk = B / (256 * per);
+    uint32_t log_per = 0;
+    while (log_per < 5 && ((uint32_t)BR_THREADS << (log_per + 1)) <= B) log_per++;
+    const uint32_t per = 1u << log_per;
+    if (B % (BR_THREADS * per)) return fail(ctx, B2R_ERR_INVALID, "msm: bucket count not a multiple of the reduce tile");
+    const uint32_t nblk = B / (BR_THREADS * per);
 
     // carve the work arena
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
     size_t o_cnt = carve(G * B * 4), o_off = carve(G * (B + 1) * 4), o_cur = carve(G * B * 4);
-    size_t o_ent = carve(G * ent_cap * 4);
+    size_t o_ent = carve(G * ent_cap * 4), o_key = carve(G * ent_cap * 4);
     size_t o_bk = carve(G * B * sizeof(xyzz_t));
     size_t o_ka = carve(G * slotsA * 4), o_pa = carve(G * slotsA * sizeof(xyzz_t));
     size_t o_kb = carve(G * slotsB * 4), o_pb = carve(G * slotsB * sizeof(xyzz_t));
@@ -410,6 +461,7 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     uint32_t* off = (uint32_t*)(base + o_off);
     uint32_t* cur = (uint32_t*)(base + o_cur);
     uint32_t* ent = (uint32_t*)(base + o_ent);
+    uint32_t* key = (uint32_t*)(base + o_key);
     xyzz_t* bk = (xyzz_t*)(base + o_bk);
     uint32_t* ka = (uint32_t*)(base + o_ka);
     xyzz_t* pa = (xyzz_t*)(base + o_pa);
@@ -422,17 +474,17 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     B2R_CUDA(ctx, cudaMemsetAsync(bk, 0, G * B * sizeof(xyzz_t), st));
     dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
     { KTimer kt(ctx, "msm_count", (double)G * n);
-    k_digits<false><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cnt, nullptr, 0); }
+    k_digits<false><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cnt, nullptr, nullptr, 0); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_scan");
     k_scan<<<(unsigned)G, 1024, 0, st>>>(cnt, off, cur, B); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_scatter", (double)G * n);
-    k_digits<true><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cur, ent, ent_cap); }
+    k_digits<true><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cur, ent, key, ent_cap); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_accum_entries", (double)G * n);
-    k_accum_entries<<<dim3((nch1 + 127) / 128, (unsigned)G), 128, 0, st>>>(bs->table, ent, ent_cap, off, B, L1, nch1, bk,
-                                                                          ka, pa, slotsA); }
+    k_accum_entries<L1><<<dim3((nch1 + 127) / 128, (unsigned)G), 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa,
+                                                                              slotsA); }
     B2R_LAUNCH_CHECK(ctx);
     // upper levels: ping-pong slot lists until one chunk remains
     const uint32_t* ik = ka;
@@ -446,8 +498,7 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
         xyzz_t* op = to_b ? pb : pa;
         size_t out_stride = to_b ? slotsB : slotsA;
         { KTimer kt(ctx, "msm_accum_slots");
-        k_accum_slots<<<dim3((nch + 127) / 128, (unsigned)G), 128, 0, st>>>(ik, ip, in_stride, M, L2, nch, B, bk, ok, op,
-                                                                           out_stride); }
+        k_accum_slots<L2><<<dim3((nch + 127) / 128, (unsigned)G), 128, 0, st>>>(ik, ip, in_stride, M, nch, B, bk, ok, op, out_stride); }
         B2R_LAUNCH_CHECK(ctx);
         if (nch == 1) break;
         ik = ok;
@@ -457,7 +508,7 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
         to_b = !to_b;
     }
     { KTimer kt(ctx, "msm_bucket_reduce");
-    k_bucket_reduce<<<dim3(nblk, (unsigned)G), 256, 256 * sizeof(xyzz_t), st>>>(bk, B, per, blk, nblk); }
+    k_bucket_reduce<<<dim3(nblk, (unsigned)G), BR_THREADS, 0, st>>>(bk, B, per, log_per, blk, nblk); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_final");
     k_final<<<(unsigned)G, 32, 0, st>>>(blk, nblk, out_dev); }
@@ -469,7 +520,7 @@ static size_t msm_group_bytes(const b2r_bases* bs, size_t n) {
     const uint32_t W = bs->W, B = 1u << (bs->c - 1);
     size_t ent_cap = n * W;
     size_t nch1 = (ent_cap + 31) / 32, slotsA = 2 * nch1, slotsB = 2 * ((slotsA + 15) / 16);
-    return 3 * (size_t)B * 4 + ent_cap * 4 + (size_t)B * 128 + (slotsA + slotsB) * 132 + 4096 * 8;
+    return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + 4096 * 8;
 }
 
 int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev) {

@@ -284,3 +284,9 @@ void orc_g1_scalar_muls(const fe* scalars, g1a* out, size_t n, int nthreads) {
     run_parallel(smul_fn, &j, nthreads);
 }
 void orc_fr_mul_array(fe* a, const fe* b, size_t n) { for (size_t i = 0; i < n; i++) a[i] = fe_mul(&FR, &a[i], &b[i]); }
+
+/* bulk conversions for the Python oracle prover: canonical <-> Montgomery, in place */
+void orc_fr_to_mont_array(fe* a, size_t n) { for (size_t i = 0; i < n; i++) { uint64_t c[4]; memcpy(c, a[i].l, 32); a[i] = fe_to_mont(&FR, c); } }
+void orc_fr_from_mont_array(fe* a, size_t n) { for (size_t i = 0; i < n; i++) { uint64_t c[4]; fe_from_mont(&FR, &a[i], c); memcpy(a[i].l, c, 32); } }
+void orc_fq_to_mont_array(fe* a, size_t n) { for (size_t i = 0; i < n; i++) { uint64_t c[4]; memcpy(c, a[i].l, 32); a[i] = fe_to_mont(&FQ, c); } }
+void orc_fq_from_mont_array(fe* a, size_t n) { for (size_t i = 0; i < n; i++) { uint64_t c[4]; fe_from_mont(&FQ, &a[i], c); memcpy(a[i].l, c, 32); } }

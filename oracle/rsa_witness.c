@@ -671,6 +671,25 @@ int orc_bigint_op(orc_table* t, int op, int bits_len, const uint64_t* a_words, c
     return c->failed ? -1 : nout;
 }
 
+/* keygen-side exports for the oracle prover (oracle/plonk.py): fixed columns, range selectors/tags,
+ * copy constraints, bits per lookup tag */
+void orc_table_fixed(const orc_table* t, fe* out) {
+    for (int i = 0; i < NFIX; i++) memcpy(out + (size_t)i * t->c.nrows, t->c.fix[i], t->c.nrows * sizeof(fe));
+}
+void orc_table_range(const orc_table* t, uint8_t* out /* [4][nrows]: s_comp, tag_comp, s_over, tag_over */) {
+    size_t n = t->c.nrows;
+    memcpy(out, t->c.s_comp, n); memcpy(out + n, t->c.tag_comp, n); memcpy(out + 2 * n, t->c.s_over, n); memcpy(out + 3 * n, t->c.tag_over, n);
+}
+size_t orc_table_copies(const orc_table* t, uint32_t* out, size_t cap) {
+    size_t n = t->c.ncopies < cap ? t->c.ncopies : cap;
+    if (out) memcpy(out, t->c.copies, n * 4 * sizeof(uint32_t));
+    return t->c.ncopies;
+}
+void orc_table_tag_bits(const orc_table* t, int* out /* [16], bits of tag i, 0 = unused */) {
+    for (int i = 0; i < 16; i++) out[i] = 0;
+    for (int b = 1; b < 80; b++) if (t->c.tag_of_bits[b] && t->c.tag_of_bits[b] < 16) out[t->c.tag_of_bits[b]] = b;
+}
+
 /* layout digest, compared with the product's host-side circuit recorder (tests/test_host_circuit.py):
  * out[0] = rows used, out[1] = order-independent hash of all fixed cells (canonical values),
  * out[2] = number of copy constraints, out[3] = order-independent hash of the copy constraints,

@@ -38,7 +38,7 @@ def gen_key(bits, j):
 
 if __name__ == "__main__":
     out = {}
-    for bits, count in ((1024, 4), (2048, 8), (4096, 4)):
+    for bits, count in ((512, 2), (1024, 4), (2048, 8), (4096, 4)):
         out[str(bits)] = [gen_key(bits, j) for j in range(count)]
         print(bits, "done")
     json.dump(out, open(os.path.join(HERE, "rsa_keys.json"), "w"), indent=1)

@@ -65,6 +65,10 @@ def main():
             scb = torch.from_numpy(random_fr_np(n * a.batch, 7).view(np.int64)).cuda()
             best, avg = timeit(lambda: ctx.msm_batch_dev(bs, scb.data_ptr(), a.batch, n, out.data_ptr()))
             print(f"msm 2^{L} x{a.batch} uniform: best {best:.3f} ms ({best/a.batch:.3f} each)", flush=True)
+            ctx.profile_enable(True); ctx.profile_dump(clear=True)
+            ctx.msm_batch_dev(bs, scb.data_ptr(), a.batch, n, out.data_ptr())
+            print("   per kernel (ms):", {k: round(v[0], 3) for k, v in ctx.profile_dump(clear=True).items()}, flush=True)
+            ctx.profile_enable(False)
             # advice-like skew: 40% zero, 30% one, 20% bytes, 9% 64-bit, 1% full
             rng = np.random.default_rng(3)
             canon = np.zeros((n * a.batch, 4), dtype=np.uint64)
@@ -81,6 +85,10 @@ def main():
             sk = torch.from_numpy(np.tile(mont, (a.batch, 1)).view(np.int64)).cuda()
             best, avg = timeit(lambda: ctx.msm_batch_dev(bs, sk.data_ptr(), a.batch, n, out.data_ptr()))
             print(f"msm 2^{L} x{a.batch} advice-like skew: best {best:.3f} ms ({best/a.batch:.3f} each)", flush=True)
+            ctx.profile_enable(True); ctx.profile_dump(clear=True)
+            ctx.msm_batch_dev(bs, sk.data_ptr(), a.batch, n, out.data_ptr())
+            print("   per kernel (ms):", {k: round(v[0], 3) for k, v in ctx.profile_dump(clear=True).items()}, flush=True)
+            ctx.profile_enable(False)
         bs.free()
     print("launches", ctx.launch_count)
 
