@@ -70,6 +70,11 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_prog_info": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
         "b2r_rsa_witness_batch": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
         "b2r_rsa_witness_batch_dev": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
+        "b2r_rsa_keygen": [vp, vp, vp, vp, C.POINTER(vp)],
+        "b2r_pk_free": [vp, vp],
+        "b2r_pk_info": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)],
+        "b2r_pk_export_vk": [vp, vp, vp, vp],
+        "b2r_rsa_prove_batch": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the ABI symbol is missing: loud by design
@@ -258,6 +263,12 @@ class Context:
         self._ck(fn(self.h, prog.h, g_lagrange.h, C.c_void_p(n_ptr), C.c_void_p(s_ptr), C.c_void_p(h_ptr), batch, blind_seed,
                     prog.k, ext_k, C.c_void_p(advice_dptr), C.c_void_p(ext_dptr or 0), C.c_void_p(cm_ptr), C.c_void_p(valid_ptr)))
 
+    # -- keygen + full prover (keygen_vk / keygen_pk / create_proof of the reference's bench)
+    def rsa_keygen(self, prog: "RsaProgram", g: "Bases", g_lagrange: "Bases") -> "ProvingKey":
+        h = C.c_void_p()
+        self._ck(self.lib.b2r_rsa_keygen(self.h, prog.h, g.h, g_lagrange.h, C.byref(h)))
+        return ProvingKey(self, h, prog)
+
     # -- RSA witness (Circuit::synthesize of the pkcs1v15 circuit)
     def rsa_program(self, bits_len: int, k: int, e: int = 65537) -> "RsaProgram":
         e_le = np.frombuffer(e.to_bytes((e.bit_length() + 7) // 8, "little"), dtype=np.uint8).copy()
@@ -279,6 +290,45 @@ class Bases:
     def free(self):
         if self.h:
             self.ctx._ck(self.ctx.lib.b2r_bases_free(self.ctx.h, self.h))
+            self.h = None
+
+
+class ProvingKey:
+    """keygen_pk output, resident on the GPU (mirrors b2r_pk)."""
+
+    def __init__(self, ctx: Context, h, prog: "RsaProgram"):
+        self.ctx, self.h, self.prog = ctx, h, prog
+        k, ek, nf, ns, pb = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+        ctx._ck(ctx.lib.b2r_pk_info(h, C.byref(k), C.byref(ek), C.byref(nf), C.byref(ns), C.byref(pb)))
+        self.k, self.ext_k, self.num_fixed, self.num_sigma, self.proof_bytes = k.value, ek.value, nf.value, ns.value, pb.value
+
+    def export_vk(self):
+        """-> (fixed commitments uint64[num_fixed, 8], sigma commitments uint64[num_sigma, 8], transcript_repr uint64[4])"""
+        f = np.zeros((self.num_fixed, 8), dtype=np.uint64)
+        s = np.zeros((self.num_sigma, 8), dtype=np.uint64)
+        t = np.zeros(4, dtype=np.uint64)
+        self.ctx._ck(self.ctx.lib.b2r_pk_export_vk(self.h, _host_ptr(f), _host_ptr(s), _host_ptr(t)))
+        return f, s, t
+
+    def prove_batch(self, n_limbs, sig_limbs, hash_limbs, seed: int):
+        """create_proof for a batch -> (proofs uint8[batch, proof_bytes], status uint8[batch])"""
+        n_limbs = np.ascontiguousarray(n_limbs, dtype=np.uint64)
+        sig_limbs = np.ascontiguousarray(sig_limbs, dtype=np.uint64)
+        hash_limbs = np.ascontiguousarray(hash_limbs, dtype=np.uint64)
+        batch = n_limbs.shape[0]
+        proofs = np.zeros((batch, self.proof_bytes), dtype=np.uint8)
+        status = np.zeros(batch, dtype=np.uint8)
+        self.prove_batch_raw(n_limbs.ctypes.data, sig_limbs.ctypes.data, hash_limbs.ctypes.data, batch, seed, proofs.ctypes.data,
+                             status.ctypes.data)
+        return proofs, status
+
+    def prove_batch_raw(self, n_ptr: int, s_ptr: int, h_ptr: int, batch: int, seed: int, proofs_ptr: int, status_ptr: int):
+        self.ctx._ck(self.ctx.lib.b2r_rsa_prove_batch(self.ctx.h, self.h, C.c_void_p(n_ptr), C.c_void_p(s_ptr), C.c_void_p(h_ptr), batch,
+                                                      seed, C.c_void_p(proofs_ptr), C.c_void_p(status_ptr)))
+
+    def free(self):
+        if self.h:
+            self.ctx._ck(self.ctx.lib.b2r_pk_free(self.ctx.h, self.h))
             self.h = None
 
 

@@ -19,52 +19,15 @@
 
 #include "circuit.hpp"
 #include "ctx.hpp"
+#include "devutil.cuh"
+#include "prog.hpp"
 
 using namespace b2r;
 using namespace b2r::circuit;
 
-struct LevelRange {
-    uint32_t start, end;    // node ids
-    uint32_t bstart, bend;  // range in big_nodes
-};
-
-struct b2r_prog {
-    uint32_t bits_len = 0, num_limbs = 0, k = 0;
-    uint32_t rows_used = 0, num_values = 0, num_levels = 0;
-    int32_t is_valid_vid = -1;
-    uint32_t num_inputs = 0;
-    // device
-    Node* d_nodes = nullptr;
-    LevelRange* d_levels = nullptr;
-    uint32_t* d_big_nodes = nullptr;
-    BigOp* d_big_ops = nullptr;
-    uint32_t* d_big_inputs = nullptr;
-    fe_t* d_consts = nullptr;
-    int32_t* d_cellmap = nullptr;  // [5][2^k]
-    uint32_t max_big_words = 0;
-    // host copies kept for keygen / inspection
-    std::vector<std::array<uint32_t, NUM_FIXED>> fixed;
-    std::vector<std::array<uint8_t, 4>> range_tags;
-    std::vector<std::array<uint32_t, 4>> copies;
-    std::vector<U256> constants;
-};
-
 namespace b2r {
 
 // ---- device helpers -------------------------------------------------------------------------
-__device__ __forceinline__ fe_t ldv(const fe_t* p) {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = q[0], b = q[1];
-    fe_t r;
-    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
-    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
-    return r;
-}
-__device__ __forceinline__ void stv(fe_t* p, const fe_t& v) {
-    uint4* q = reinterpret_cast<uint4*>(p);
-    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-}
 __device__ __forceinline__ fe_t fe_from_u64_dev(uint64_t v) {
     fe_t c = Fr::zero();
     c.l[0] = (uint32_t)v;
@@ -346,42 +309,22 @@ __global__ void __launch_bounds__(1024) k_witness_eval(const WitnessArgs A) {
     }
 }
 
-// seeded blinding stream (documented in DESIGN.md; restated by tests): splitmix64 over
-// (seed, instance, column, row, word), top two bits cleared, one conditional subtraction of r.
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
-__device__ __forceinline__ fe_t blind_value(uint64_t seed, uint32_t p, uint32_t col, uint32_t row) {
-    fe_t r;
-    uint64_t base = splitmix64(seed ^ splitmix64(((uint64_t)p << 32) | ((uint64_t)col << 28) | row));
-    for (int j = 0; j < 4; j++) {
-        uint64_t w = splitmix64(base + j);
-        r.l[2 * j] = (uint32_t)w;
-        r.l[2 * j + 1] = (uint32_t)(w >> 32);
-    }
-    r.l[7] &= 0x3fffffffu;
-    Fr::final_sub(r.l);
-    return r;
-}
-
 __global__ void __launch_bounds__(256)
 k_witness_emit(const int32_t* __restrict__ cellmap, const fe_t* __restrict__ values, uint32_t num_values, uint32_t k,
-               uint32_t usable_rows, uint64_t blind_seed, uint32_t p_base, fe_t* __restrict__ advice) {
+               uint32_t usable_rows, uint64_t blind_seed, uint32_t p_base, fe_t* __restrict__ advice, size_t p_stride,
+               size_t col_stride) {
     const uint32_t n = 1u << k;
     uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t col = blockIdx.y, p = blockIdx.z;
     if (row >= n) return;
     fe_t v;
     if (row >= usable_rows) {
-        v = blind_seed ? blind_value(blind_seed, p_base + p, col, row) : Fr::zero();
+        v = blind_seed ? blind_value(blind_seed, p_base + p, ST_ADVICE + col, row) : Fr::zero();
     } else {
         int32_t id = cellmap[(size_t)col * n + row];
         v = id < 0 ? Fr::zero() : ldv(values + (size_t)p * num_values + id);
     }
-    stv(advice + ((size_t)p * NUM_ADVICE + col) * n + row, v);
+    stv(advice + (size_t)p * p_stride + (size_t)col * col_stride + row, v);
 }
 
 }  // namespace b2r
@@ -469,6 +412,8 @@ static int32_t finalize_program(b2r_ctx* ctx, RegionCtx& rc, AssignedValue is_va
     prog->range_tags = std::move(rc.range_tags);
     prog->copies = std::move(rc.copies);
     prog->constants = rc.constants;
+    for (int b = 1; b < 80; b++)
+        if (rc.tag_of_bits[b] > 0 && rc.tag_of_bits[b] < 16) prog->tag_bits[rc.tag_of_bits[b]] = (uint8_t)b;
     return 0;
 }
 
@@ -537,9 +482,13 @@ int32_t b2r_prog_info(const b2r_prog* prog, uint64_t* rows_used, uint64_t* num_v
     return 0;
 }
 
-static int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
-                           const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev,
-                           uint8_t* is_valid_dev, size_t p_base) {
+}  // extern "C"
+
+namespace b2r {
+// advice cell (p, col, row) is written to advice_dev[p * p_stride + col * col_stride + row]
+int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
+                    const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev,
+                    uint8_t* is_valid_dev, size_t p_base, size_t p_stride, size_t col_stride) {
     if (!ctx) return B2R_ERR_INVALID;
     if (!prog || !n_limbs_dev || !sig_limbs_dev || !hash_limbs_dev || !advice_dev || !is_valid_dev)
         return fail(ctx, B2R_ERR_INVALID, "rsa_witness: null pointer");
@@ -577,16 +526,21 @@ static int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n
         dim3 grid((n + 255) / 256, NUM_ADVICE, (unsigned)g);
         KTimer kt_emit(ctx, "witness_emit", (double)g);
         k_witness_emit<<<grid, 256, 0, ctx->stream>>>(prog->d_cellmap, values, prog->num_values, prog->k, n - BLINDING_ROWS, blind_seed,
-                                                      (uint32_t)(p_base + p0), (fe_t*)advice_dev + p0 * NUM_ADVICE * n);
+                                                      (uint32_t)(p_base + p0), (fe_t*)advice_dev + p0 * p_stride, p_stride, col_stride);
         B2R_LAUNCH_CHECK(ctx);
     }
     return 0;
 }
+}  // namespace b2r
+
+extern "C" {
 
 int32_t b2r_rsa_witness_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
                                   const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev,
                                   uint8_t* is_valid_dev) {
-    return witness_run(ctx, prog, n_limbs_dev, sig_limbs_dev, hash_limbs_dev, batch, blind_seed, advice_dev, is_valid_dev, 0);
+    if (!prog) return ctx ? fail(ctx, B2R_ERR_INVALID, "rsa_witness: null pointer") : B2R_ERR_INVALID;
+    const size_t n = (size_t)1 << prog->k;
+    return witness_run(ctx, prog, n_limbs_dev, sig_limbs_dev, hash_limbs_dev, batch, blind_seed, advice_dev, is_valid_dev, 0, NUM_ADVICE * n, n);
 }
 
 int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs, const uint64_t* sig_limbs,
@@ -612,7 +566,7 @@ int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t
     B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * 4 * 8, cudaMemcpyHostToDevice, ctx->stream));
     for (size_t p0 = 0; p0 < batch; p0 += G) {
         size_t g = std::min(G, batch - p0);
-        B2R_TRY(witness_run(ctx, prog, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * 4, g, blind_seed, (b2r_fr*)d_adv, d_valid + p0, p0));
+        B2R_TRY(witness_run(ctx, prog, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * 4, g, blind_seed, (b2r_fr*)d_adv, d_valid + p0, p0, NUM_ADVICE * n, n));
         B2R_CUDA(ctx, cudaMemcpyAsync((char*)advice + p0 * per_adv, d_adv, g * per_adv, cudaMemcpyDeviceToHost, ctx->stream));
         B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }

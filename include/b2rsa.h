@@ -38,6 +38,7 @@ typedef struct { b2r_fq x, y, z; } b2r_g1;
 typedef struct b2r_ctx b2r_ctx;
 typedef struct b2r_prog b2r_prog;   /* a recorded witness program (static circuit layout) */
 typedef struct b2r_bases b2r_bases; /* a resident, pre-processed MSM base set */
+typedef struct b2r_pk b2r_pk;       /* proving key of the RSA circuit (fixed / permutation polynomials, cosets, vk) */
 
 enum b2r_status {
     B2R_OK = 0,
@@ -169,6 +170,25 @@ int32_t b2r_rsa_commit_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const b2r_b
                                  const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed,
                                  uint32_t k, uint32_t ext_k, b2r_fr* advice_dev, b2r_fr* ext_dev,
                                  b2r_g1_affine* commitments_dev, uint8_t* is_valid_dev);
+
+/* ---- keygen and the full prover ---------------------------------------
+ * b2r_rsa_keygen replaces keygen_vk + keygen_pk for the pkcs1v15 circuit (reference benches/bench.rs:236-237):
+ * fixed columns, lookup table, permutation (sigma) polynomials, their coefficient / extended-coset forms and
+ * the verifying-key commitments, all resident on the GPU.  `g` / `g_lagrange` are the two SRS base sets
+ * (b2r_srs_setup or b2r_bases_register) and must outlive the key, as must `prog`. */
+int32_t b2r_rsa_keygen(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g, const b2r_bases* g_lagrange, b2r_pk** out);
+int32_t b2r_pk_free(b2r_ctx* ctx, b2r_pk* pk);
+int32_t b2r_pk_info(const b2r_pk* pk, uint32_t* k, uint32_t* ext_k, uint32_t* num_fixed, uint32_t* num_sigma, uint64_t* proof_bytes);
+/* verifying key: num_fixed fixed-column commitments, num_sigma permutation commitments, vk transcript scalar */
+int32_t b2r_pk_export_vk(const b2r_pk* pk, b2r_g1_affine* fixed_commitments, b2r_g1_affine* sigma_commitments, b2r_fr* transcript_repr);
+/* Replaces create_proof::<KZGCommitmentScheme<Bn256>, ProverGWC<_>, Challenge255<_>, _, Blake2bWrite<..>, _>
+ * (reference benches/bench.rs:319-331) for `batch` independent instances: HOST inputs as in
+ * b2r_rsa_witness_batch, HOST outputs: proofs = batch x proof_bytes (b2r_pk_info), status = batch bytes
+ * (1 = proof of a valid signature; 0 = the witness does not satisfy the circuit, the proof will not verify;
+ * 0xFF = the reference's synthesize would have panicked; 0xFE = a range-checked cell is out of range).
+ * `seed` (non-zero) keys the blinding stream that stands in for the reference's OsRng. */
+int32_t b2r_rsa_prove_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs,
+                            const uint64_t* hash_limbs, size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status);
 
 #ifdef __cplusplus
 }

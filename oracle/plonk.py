@@ -679,6 +679,12 @@ def verify_proof(pk, srs_secret, proof):
     return ok
 
 
+def vk_from_commitments(k, fixed_commitments, sigma_commitments, transcript_repr):
+    """the part of the key verify_proof needs, from an exported verifying key (points as (x, y) / None)"""
+    return {"k": k, "dom": Domain(k), "fixed_commitments": list(fixed_commitments), "sigma_commitments": list(sigma_commitments),
+            "transcript_repr": transcript_repr}
+
+
 def proof_length(k=None):
     nsets = (len(PERM_COLUMNS) + CHUNK - 1) // CHUNK
     points = NUM_ADVICE + 2 * len(LOOKUPS) + nsets + len(LOOKUPS) + 1 + 4 + 4

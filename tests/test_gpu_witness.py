@@ -125,7 +125,7 @@ def test_blinding_rows(prog2048):
     for p in range(2):
         for col in (0, 4):
             for row in (n - 6, n - 1):
-                base = _splitmix64(seed ^ _splitmix64((p << 32) | (col << 28) | row))
+                base = _splitmix64(seed ^ _splitmix64((p << 40) | (col << 28) | row))
                 words = [_splitmix64((base + j) & ((1 << 64) - 1)) for j in range(4)]
                 x = sum(w << (64 * j) for j, w in enumerate(words)) & ((1 << 254) - 1)
                 if x >= O.R_MOD:
