@@ -1,23 +1,23 @@
-#!/usr/bin/env python
-"""bench.py - RSA-2048 pkcs1v15 proofs/sec at k=17 over the prover hot path, on N B200s.
+"""bench.py - RSA-2048 pkcs1v15 proofs/sec at k=17 on N B200s (BASELINE.json configs[1]).
 
-One "step" = one pass of the hot path over a batch of 64 synthetic RSA-2048 instances per GPU
-(BASELINE.json configs[1]):  witness synthesis (5 advice columns x 2^17 per instance) ->
-commit_lagrange of every advice column (batched Pippenger MSM over the resident g_lagrange
-table) -> lagrange_to_coeff (iNTT 2^17) -> coeff_to_extended (coset NTT to 2^19).
-This is what SURVEY.md section 8 scopes as hot paths (a) + (b) for the advice columns; the rest
-of halo2's create_proof (lookup / permutation arguments, quotient, multiopen) is "next" (8f)
-and is NOT in the step - the workload string says so.
+One "step" = ONE COMPLETE PROOF for each of 64 synthetic RSA-2048 instances per GPU, i.e. the reference bench's
+create_proof (benches/bench.rs:319-331) for a batch: witness synthesis -> 5 advice commitments -> lookup
+permutations (10 commitments) -> permutation / lookup grand products (7) + random polynomial -> 22 x
+(lagrange_to_coeff 2^17, coeff_to_extended 2^19) -> quotient on the 2^19 coset -> 4 h commitments ->
+58 evaluations -> GWC multiopen (4 commitments): 31 MSMs of 2^17 points and 45 NTTs per proof, with the
+Blake2b transcripts on the host between the phases.  Output = 64 proofs of 2848 bytes.
 
-  value : instances / s with the inputs resident in HBM (device-timed, CUDA events)
-  e2e   : the same through the reference-facing C-ABI call b2r_rsa_commit_batch with pinned
-          HOST inputs and HOST outputs (h2d + d2h inside the timed region)
-  --impl reference : the CPU arm.  The reference is Rust and no cargo/rustc exists in this
-          image, so this times oracle/ (this repo's C restatement of the reference's CPU
-          algorithms: sequential synthesize, best_multiexp, best_fft) on all host cores.
+  value : proofs / s with the instance inputs resident in HBM (b2r_rsa_prove_batch_dev; CUDA events)
+  e2e   : the same through the reference-facing C-ABI call b2r_rsa_prove_batch with pinned HOST inputs
+          (h2d inside the timed region; the proofs always come back to the host)
+  --impl reference : the CPU arm.  The reference is Rust and no cargo/rustc exists in this image, so this
+          times oracle/ (this repo's C restatement of the reference's CPU algorithms: sequential synthesize,
+          best_multiexp, best_fft) on all host cores, for the MSM / FFT / witness work of one proof; the
+          prover glue (quotient evaluation, grand products, evaluations) is NOT included, so the CPU figure
+          is an upper bound on the CPU's proofs/s and the GPU/CPU ratio a lower bound.
 
-Multi-GPU (torchrun, one rank per GPU): instances are independent, each rank proves its own
-64, then ONE NCCL all_gather of the commitments (20 KB per rank); scaling = weak.
+Multi-GPU (torchrun, one rank per GPU): instances are independent, each rank proves its own 64, then ONE
+NCCL all_gather of the proofs (they carry the commitments; 182 KB per rank); scaling = weak.
 """
 import argparse
 import json
@@ -35,8 +35,10 @@ import numpy as np  # noqa: E402
 
 BITS, K, EXT_K, BATCH = 2048, 17, 19, 64
 NCOL = 5
-METRIC = "RSA-2048 pkcs1v15 proofs/sec at k=17 (prover hot path: witness + advice commit + iNTT + coset NTT)"
-WORKLOAD = "rsa2048_e65537_k17_batch64_per_gpu: witness(5 advice cols x 2^17) + commit_lagrange(5 MSM 2^17) + lagrange_to_coeff(5) + coeff_to_extended(5 x 2^19) per instance"
+MSM_PER_PROOF, INTT_PER_PROOF, COSET_PER_PROOF = 31, 22, 22
+METRIC = "RSA-2048 pkcs1v15 proofs/sec at k=17"
+WORKLOAD = ("rsa2048_e65537_k17_batch64_per_gpu: full create_proof per instance (witness, 31 MSM 2^17, 22 iNTT 2^17, "
+            "22 coset NTT 2^19 + 1 coset iNTT 2^19, lookups, permutation, quotient, 58 evals, GWC multiopen, Blake2b transcript)")
 MSM_BYTES_PER_TERM = 96  # 32 B scalar + 64 B affine base
 
 
@@ -96,9 +98,11 @@ class ClockSampler:
 
 
 def cpu_port_step(samples, threads):
-    """the CPU path (oracle 'port'): returns seconds for `samples` instances, sequentially, each:
-    single-threaded synthesize (as the reference), then 5 x (best_multiexp, lagrange_to_coeff,
-    coeff_to_extended) on `threads` host threads"""
+    """the CPU arm (oracle 'port'): seconds for the MSM / FFT / witness work of `samples` full proofs, sequentially:
+    single-threaded synthesize (as the reference), then on `threads` host threads 31 best_multiexp of 2^17 terms
+    (5 real advice columns; 10 permuted-lookup-like columns = 40 % full-size scalars, 60 % zero, which is what
+    theta-compressed range rows look like; 16 uniform: grand products, random poly, h pieces, GWC witnesses),
+    22 lagrange_to_coeff, 22 coeff_to_extended and 1 extended_to_coeff."""
     import cpu_oracle as CO
     import rsa_fixtures as RF
     st = cpu_port_state(threads)
@@ -111,9 +115,15 @@ def cpu_port_step(samples, threads):
         adv = t.advice()
         t.free()
         for col in range(NCOL):
-            CO.best_multiexp(adv[col], st["bases"], threads)
-            co = CO.lagrange_to_coeff(adv[col], K, threads)
+            CO.best_multiexp(adv[col], st["gl"], threads)
+        for j in range(10):
+            CO.best_multiexp(st["lookup_like"], st["gl"], threads)
+        for j in range(16):
+            CO.best_multiexp(st["uniform"], st["g"] if j >= 7 else st["gl"], threads)
+        for j in range(INTT_PER_PROOF):
+            co = CO.lagrange_to_coeff(adv[j % NCOL] if j < NCOL else st["uniform"], K, threads)
             CO.coeff_to_extended(co, K, EXT_K, threads)
+        CO.extended_to_coeff(st["ext"], EXT_K, threads)
     return time.perf_counter() - t0
 
 
@@ -124,9 +134,15 @@ def cpu_port_state(threads):
     global _cpu_state
     if _cpu_state is None:
         import cpu_oracle as CO
+        from util import random_fr_np
         CO.build()
+        n = 1 << K
         # any 2^17 valid affine points serve as timing bases for the CPU leg (cost does not depend on them)
-        _cpu_state = {"bases": CO.g1_multiples(1 << K, threads)}
+        bases = CO.g1_multiples(n, threads)
+        uni = random_fr_np(n, 11)
+        look = uni.copy()
+        look[np.random.default_rng(5).random(n) < 0.6] = 0
+        _cpu_state = {"g": bases, "gl": bases, "uniform": uni, "lookup_like": look, "ext": random_fr_np(1 << EXT_K, 12)}
     return _cpu_state
 
 
@@ -148,9 +164,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": 1, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 limbs (BN254 Fr/Fq Montgomery, integer)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_per_step": f"{sample} instance (bounded sample of the 64-instance batch)"},
+        "config": {"workload": WORKLOAD, "sample_per_step": f"{sample} proof (bounded sample of the 64-instance batch)"},
         "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} instance per step x {args.steps} steps; synthesize on 1 thread, MSM/FFT on {threads} threads"},
+                         "sample": f"{sample} proof per step x {args.steps} steps: synthesize on 1 thread + 31 MSM / 45 FFT on {threads} threads; prover glue excluded (upper bound on CPU proofs/s)"},
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Rust (no cargo/rustc in this image): timed arm is oracle/ - the C restatement of its CPU algorithms",
     }
@@ -188,40 +204,42 @@ def main():
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)  # torch's default stream has handle 0; the library needs a real stream to share
 
+    import b2rsa.shard as shard
     ctx = b2rsa.Context(local)
     ctx.set_stream(side.cuda_stream)
-    batch, n, next_ = args.batch, 1 << K, 1 << EXT_K
+    batch, n = args.batch, 1 << K
     prog = ctx.rsa_program(BITS, K)
     import bn254 as O
     from util import fr_to_np
-    _, gl = ctx.srs_setup(K, fr_to_np([O.srs_secret(K)])[0])
+    g, gl = ctx.srs_setup(K, fr_to_np([O.srs_secret(K)])[0])
+    pk = ctx.rsa_keygen(prog, g, gl)
+    pb = pk.proof_bytes
 
     # rank r proves instances [r*batch, (r+1)*batch)
-    nl, sl, hl = RF.batch(BITS, batch, start=rank * batch)
+    mine = shard.instance_range(rank, world, world * batch)
+    nl, sl, hl = RF.batch(BITS, batch, start=mine.start)
     h_n = torch.from_numpy(nl.view(np.int64)).pin_memory()
     h_s = torch.from_numpy(sl.view(np.int64)).pin_memory()
     h_h = torch.from_numpy(hl.view(np.int64)).pin_memory()
     d_n, d_s, d_h = h_n.to(dev), h_s.to(dev), h_h.to(dev)
-    adv = torch.empty(batch * NCOL * n * 4, dtype=torch.int64, device=dev)       # 1.34 GB: larger than L2
-    ext = torch.empty(batch * NCOL * next_ * 4, dtype=torch.int64, device=dev)   # 5.4 GB
-    d_cm = torch.zeros(batch * NCOL * 8, dtype=torch.int64, device=dev)
-    d_valid = torch.zeros(batch, dtype=torch.uint8, device=dev)
-    h_cm = torch.zeros(batch * NCOL * 8, dtype=torch.int64).pin_memory()
-    h_valid = torch.zeros(batch, dtype=torch.uint8).pin_memory()
-    gathered = torch.zeros(world * batch * NCOL * 8, dtype=torch.int64, device=dev) if world > 1 else None
+    h_proofs = torch.zeros(batch * pb, dtype=torch.uint8).pin_memory()
+    h_status = torch.zeros(batch, dtype=torch.uint8).pin_memory()
+    d_proofs = torch.zeros((batch, pb // 8), dtype=torch.int64, device=dev)
+    seed = 0xB200 + rank
+
+    def finish():
+        if world > 1:
+            d_proofs.copy_(h_proofs.view(torch.int64).view(batch, pb // 8), non_blocking=True)
+            shard.gather_commitments(d_proofs, world * batch)
 
     def step_dev():
-        ctx.rsa_commit_batch_raw(prog, gl, d_n.data_ptr(), d_s.data_ptr(), d_h.data_ptr(), batch, EXT_K, adv.data_ptr(),
-                                 ext.data_ptr(), d_cm.data_ptr(), d_valid.data_ptr(), blind_seed=0xB200 + rank)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_cm)
+        pk.prove_batch_raw(d_n.data_ptr(), d_s.data_ptr(), d_h.data_ptr(), batch, seed, h_proofs.data_ptr(), h_status.data_ptr(),
+                           inputs_on_device=True)
+        finish()
 
     def step_e2e():
-        ctx.rsa_commit_batch_raw(prog, gl, h_n.data_ptr(), h_s.data_ptr(), h_h.data_ptr(), batch, EXT_K, adv.data_ptr(),
-                                 ext.data_ptr(), h_cm.data_ptr(), h_valid.data_ptr(), blind_seed=0xB200 + rank, host=True)
-        if world > 1:
-            d_cm.copy_(h_cm, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, d_cm)
+        pk.prove_batch_raw(h_n.data_ptr(), h_s.data_ptr(), h_h.data_ptr(), batch, seed, h_proofs.data_ptr(), h_status.data_ptr())
+        finish()
 
     def barrier():
         torch.cuda.synchronize()
@@ -237,15 +255,18 @@ def main():
             fn()
         e1.record(side)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return shard.max_over_ranks(e0.elapsed_time(e1), dev)
 
     for _ in range(args.warmup):
         step_dev()
     torch.cuda.synchronize()
-    assert d_valid.cpu().tolist() == [1] * batch, "synthetic signatures must verify"
+    assert h_status.tolist() == [1] * batch, "synthetic signatures must verify"
+    if rank == 0:  # the timed path's output is a real proof: check one against the oracle verifier
+        import plonk as PL
+        from util import np_to_fr, np_to_g1
+        f, s_, t = pk.export_vk()
+        vk = PL.vk_from_commitments(K, np_to_g1(f), np_to_g1(s_), np_to_fr(t.reshape(1, 4))[0])
+        assert PL.verify_proof(vk, O.srs_secret(K), bytes(h_proofs[:pb].numpy())), "proof rejected by the oracle verifier"
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -258,10 +279,9 @@ def main():
     ctx.profile_enable(False)
     clocks = sampler.stop()
 
-    for _ in range(2):
-        step_e2e()
+    step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    assert h_valid.tolist() == [1] * batch
+    assert h_status.tolist() == [1] * batch
 
     value = world * batch * args.steps / (ms / 1e3)
     e2e_value = world * batch * args.steps / (ms_e2e / 1e3)
@@ -269,11 +289,10 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         peak = (peaks or {}).get("hbm_gbs", 6650.0)
-        dom, (dom_ms, dom_cnt) = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 0))
         roof = None
         if "msm_accum_entries" in prof:
             kms, kcnt = prof["msm_accum_entries"]
-            terms_per_launch = batch * NCOL * n * args.steps / kcnt
+            terms_per_launch = batch * MSM_PER_PROOF * n * args.steps / kcnt
             achieved = terms_per_launch * MSM_BYTES_PER_TERM / (kms / kcnt / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": "k_accum_entries (MSM bucket accumulation)", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -285,10 +304,11 @@ def main():
             "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (BN254 Fr/Fq Montgomery, integer)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * batch, "parallelism": f"instances sharded x{world}, 1 all_gather of commitments",
-                       "l2": "inputs larger than L2 (1.34 GB advice + 5.4 GB extended per step)"},
+            "config": {"workload": WORKLOAD, "global_batch": world * batch, "proof_bytes": pb,
+                       "parallelism": f"instances sharded x{world}, 1 all_gather of the proofs",
+                       "l2": "inputs larger than L2 (the per-step polynomial arena is 17 GB)"},
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(h_n.numel() + h_s.numel() + h_h.numel()) * 8,
-                    "d2h_bytes_per_step": int(h_cm.numel()) * 8 + int(h_valid.numel()), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(h_proofs.numel()) + int(h_status.numel()), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
         }
@@ -298,7 +318,7 @@ def main():
             sample = 2
             t = cpu_port_step(sample, threads)
             line["cpu_baseline"] = {"value": sample / t, "unit": "proofs/s", "cores": threads, "kind": "port",
-                                    "sample": f"{sample} instances of the same workload, sequential; synthesize on 1 thread, best_multiexp/best_fft restatements on {threads} threads ({t:.1f} s)"}
+                                    "sample": f"MSM / FFT / witness work of {sample} full proofs, sequential: synthesize on 1 thread, 31 best_multiexp + 45 best_fft restatements per proof on {threads} threads ({t:.1f} s); prover glue excluded, so this is an upper bound on the CPU's proofs/s"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

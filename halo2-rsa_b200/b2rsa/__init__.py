@@ -75,6 +75,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_pk_info": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)],
         "b2r_pk_export_vk": [vp, vp, vp, vp],
         "b2r_rsa_prove_batch": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
+        "b2r_rsa_prove_batch_dev": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the ABI symbol is missing: loud by design
@@ -322,9 +323,11 @@ class ProvingKey:
                              status.ctypes.data)
         return proofs, status
 
-    def prove_batch_raw(self, n_ptr: int, s_ptr: int, h_ptr: int, batch: int, seed: int, proofs_ptr: int, status_ptr: int):
-        self.ctx._ck(self.ctx.lib.b2r_rsa_prove_batch(self.ctx.h, self.h, C.c_void_p(n_ptr), C.c_void_p(s_ptr), C.c_void_p(h_ptr), batch,
-                                                      seed, C.c_void_p(proofs_ptr), C.c_void_p(status_ptr)))
+    def prove_batch_raw(self, n_ptr: int, s_ptr: int, h_ptr: int, batch: int, seed: int, proofs_ptr: int, status_ptr: int,
+                        inputs_on_device: bool = False):
+        fn = self.ctx.lib.b2r_rsa_prove_batch_dev if inputs_on_device else self.ctx.lib.b2r_rsa_prove_batch
+        self.ctx._ck(fn(self.ctx.h, self.h, C.c_void_p(n_ptr), C.c_void_p(s_ptr), C.c_void_p(h_ptr), batch,
+               seed, C.c_void_p(proofs_ptr), C.c_void_p(status_ptr)))
 
     def free(self):
         if self.h:

@@ -1082,30 +1082,45 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
 
 extern "C" {
 
-int32_t b2r_rsa_prove_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs, const uint64_t* hash_limbs,
-                            size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status) {
-    if (!ctx) return B2R_ERR_INVALID;
-    if (!pk || !n_limbs || !sig_limbs || !hash_limbs || !proofs || !status) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: null pointer");
-    if (seed == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: seed must be non-zero (blinding rows)");
-    if (batch == 0) return 0;
+static int32_t prove_all(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, const uint64_t* d_s, const uint64_t* d_h, size_t batch,
+                         uint64_t seed, uint8_t* proofs, uint8_t* status) {
     uint64_t proof_bytes = 0;
     b2r_pk_info(pk, nullptr, nullptr, nullptr, nullptr, &proof_bytes);
     const size_t nl = pk->prog->num_limbs;
     // group size bounded by a memory budget (about 230 MiB of arena per proof at k = 17)
     const size_t per_proof = ((size_t)NSLOT + QD + 3 * NZ + 2 * NPOINTS) * pk->n * 32 + 4096;
     size_t G = std::max<size_t>(1, std::min<size_t>(64, ((size_t)48 << 30) / per_proof));
-    uint64_t* d_in = nullptr;
-    B2R_TRY(scratch_get(ctx, SC_MISC, batch * (2 * nl + 4) * 8 + 256, (void**)&d_in));
-    uint64_t *d_n = d_in, *d_s = d_in + batch * nl, *d_h = d_in + 2 * batch * nl;
-    B2R_CUDA(ctx, cudaMemcpyAsync(d_n, n_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
-    B2R_CUDA(ctx, cudaMemcpyAsync(d_s, sig_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
-    B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * 4 * 8, cudaMemcpyHostToDevice, ctx->stream));
     for (size_t p0 = 0; p0 < batch; p0 += G) {
         const uint32_t g = (uint32_t)std::min(G, batch - p0);
         B2R_TRY(prove_group(ctx, pk, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * 4, g, seed, (uint32_t)p0, proofs + p0 * proof_bytes, status + p0,
                             (size_t)proof_bytes));
     }
     return 0;
+}
+
+int32_t b2r_rsa_prove_batch_dev(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
+                                const uint64_t* hash_limbs_dev, size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!pk || !n_limbs_dev || !sig_limbs_dev || !hash_limbs_dev || !proofs || !status) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: null pointer");
+    if (seed == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: seed must be non-zero (blinding rows)");
+    if (batch == 0) return 0;
+    return prove_all(ctx, pk, n_limbs_dev, sig_limbs_dev, hash_limbs_dev, batch, seed, proofs, status);
+}
+
+int32_t b2r_rsa_prove_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs, const uint64_t* hash_limbs,
+                            size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!pk || !n_limbs || !sig_limbs || !hash_limbs || !proofs || !status) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: null pointer");
+    if (seed == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: seed must be non-zero (blinding rows)");
+    if (batch == 0) return 0;
+    const size_t nl = pk->prog->num_limbs;
+    uint64_t* d_in = nullptr;
+    B2R_TRY(scratch_get(ctx, SC_MISC, batch * (2 * nl + 4) * 8 + 256, (void**)&d_in));
+    uint64_t *d_n = d_in, *d_s = d_in + batch * nl, *d_h = d_in + 2 * batch * nl;
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_n, n_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_s, sig_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * 4 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return prove_all(ctx, pk, d_n, d_s, d_h, batch, seed, proofs, status);
 }
 
 }  // extern "C"

@@ -189,6 +189,10 @@ int32_t b2r_pk_export_vk(const b2r_pk* pk, b2r_g1_affine* fixed_commitments, b2r
  * `seed` (non-zero) keys the blinding stream that stands in for the reference's OsRng. */
 int32_t b2r_rsa_prove_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs,
                             const uint64_t* hash_limbs, size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status);
+/* same with the instance inputs already resident in HBM (DEVICE pointers); proofs / status are HOST buffers: the proof
+ * bytes are assembled by the per-proof transcripts on the host. */
+int32_t b2r_rsa_prove_batch_dev(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
+                                const uint64_t* hash_limbs_dev, size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,19 @@ def test_full_size_proofs_verify(ctx):
     pk.free(); g.free(); gl.free(); prog.free()
 
 
+@pytest.mark.parametrize("bits,k", [(1024, 15), (4096, 18)])
+def test_other_key_sizes_verify(ctx, bits, k):
+    """BASELINE configs[2] (RSA-4096, k=18) and the reference's own enabled bench size (RSA-1024, k=15)"""
+    prog, g, gl, pk = _setup(ctx, bits, k)
+    vk = _vk(pk)
+    nl, sl, hl = RF.batch(bits, 2)
+    proofs, status = pk.prove_batch(nl, sl, hl, seed=99)
+    assert status.tolist() == [1, 1]
+    for i in range(2):
+        assert PL.verify_proof(vk, O.srs_secret(k), bytes(proofs[i]))
+    pk.free(); g.free(); gl.free(); prog.free()
+
+
 def test_prover_argument_errors(small):
     import b2rsa
     bits, k, pk, srs, opk = small
