@@ -1,11 +1,14 @@
-// BN254 Fr / Fq arithmetic for sm_100a in a reduced radix: 9 limbs of 29 bits, Montgomery form with
-// R' = 2^261, lazily reduced.
+// EXPERIMENT (not used by the product): BN254 Fr / Fq arithmetic in a reduced radix, 9 limbs of 29 bits,
+// Montgomery form with R' = 2^261, lazily reduced.
 //
-// Why: tools/pipebench.cu measures on B200  IMAD.WIDE.U32 = 63.6 /clk/SM  but the carry-chained form
-// IMAD.WIDE.U32.X (what field.cuh's mad.lo.cc / madc.hi.cc rows compile to) = 30 /clk/SM.  With 29-bit
-// limbs a 64-bit accumulator holds a whole product-scanning column (18 products < 2^58 each), so the
-// 162 multiply-adds of one Montgomery product are plain full-rate IMAD.WIDE with no carry flags; the
-// carries are two shifts per column on the (otherwise idle) ALU pipe.
+// Hypothesis: field.cuh's carry-chained IMAD.WIDE.U32.X rows run at half the plain IMAD.WIDE rate, so a
+// carry-free product-scanning multiplier (64-bit column accumulators, 162 plain IMAD.WIDE + shifts) would win.
+// Measured on B200 (tools/pipebench.cu, profiles/r01_pipebench.md): it does not.  ncu shows IMAD.WIDE.U32 of ANY
+// form occupies the fmaheavy pipe for 4 cycles per warp instruction (32 lanes/clk/SM; 32-bit IMAD is 64), so the
+// cost of a Montgomery product is ~4 cycles x (number of 32x32->64 products): 128 for field.cuh (64 Gmul/s/GPU),
+// 171 here (53 Gmul/s).  The 32-bit-limb CIOS multiplier is already at the integer-multiplier roofline; the only
+// larger multiplier on the SM is the FP64 pipe (DFMA 64/clk/SM, separate from fmaheavy).  Kept as a record and
+// as a host-tested starting point for lazy-reduction bookkeeping.
 //
 // Representation invariants of F29<P>::el
 //   * limbs v[0..8] < 2^29 ("normalised"), value V = sum v[i] 2^(29 i) < 2^261;
