@@ -18,8 +18,8 @@
 //                 gathers from the table), complete buckets are stored, chunk-boundary
 //                 partial sums go to a slot list that the next level reduces the same
 //                 way.  Work per thread is uniform whatever the scalar distribution.
-//   5. k_bucket_reduce + k_final   sum_b (b+1) * B_b by per-thread running sums, shared
-//                 memory tree, one inversion to return the canonical affine point.
+//   5. k_br_level1/2/3   sum_b (b+1) * B_b by three levels of per-thread running sums, one
+//                 inversion to return the canonical affine point.
 // Algorithmic HBM bytes: 32 B per scalar + 64 B per gathered table point.
 #include <cuda_runtime.h>
 
@@ -331,98 +331,115 @@ k_accum_slots(const uint32_t* __restrict__ in_keys, const xyzz_t* __restrict__ i
 }
 
 // ---- sum_b (b+1) * B_b -------------------------------------------------------------------
-// CTA = 128 threads x `per` consecutive buckets.  Thread t: S_t = sum of its buckets and
-// A_t = sum (d+1) * B_{lo+d} by running sums (2 adds per bucket).  The CTA then needs
-// sum_t (A_t + t*per*S_t) + base * sum_t S_t:  sum_t t*S_t = sum_{j>=1} (suffix sum T_j) comes from a
-// shared-memory suffix scan (7 steps), so no thread multiplies by its own offset.
-static constexpr int BR_THREADS = 128;
-__global__ void __launch_bounds__(BR_THREADS, 3)
-k_bucket_reduce(const xyzz_t* __restrict__ buckets, uint32_t B, uint32_t per, uint32_t log_per, xyzz_t* block_out, uint32_t nblk) {
-    __shared__ uint4 smem_raw[BR_THREADS * sizeof(xyzz_t) / sizeof(uint4)];
-    xyzz_t* sm = reinterpret_cast<xyzz_t*>(smem_raw);
-    const uint32_t g = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
-    const xyzz_t* bk = buckets + (size_t)g * B;
-    const uint32_t base = blk * BR_THREADS * per, lo = base + tid * per;
+// Three levels of running sums, every thread busy in the two large ones (the first version combined 128 threads
+// per CTA with shared-memory scans and a one-thread double-and-add tail: 1.9x the additions, most of them in
+// nearly empty warps - profiles/r01_ncu_full_baseline.md).
+//   level 1  thread = 32 consecutive buckets:  S1_s = sum B,  A1_s = sum (d + 1) B_{32 s + d}        (2 adds / bucket)
+//   level 2  thread = 8 consecutive segments:  S2_u = sum S1, A2_u = sum d S1_{8 u + d}, P1_u = sum A1  (3 adds / segment)
+//   level 3  CTA per vector over the nu = B / 256 level-2 outputs: W = sum_u u S2_u (suffix scan + tree), sums of A2, P1
+//   result = P1 + 32 (A2 + 8 W), one inversion to affine.
+static constexpr uint32_t BR_PER1 = 32, BR_PER2 = 8, BR_T3 = 128;
+
+__global__ void __launch_bounds__(128)
+k_br_level1(const xyzz_t* __restrict__ buckets, uint32_t B, uint32_t nseg, xyzz_t* __restrict__ S1, xyzz_t* __restrict__ A1) {
+    const uint32_t g = blockIdx.y, s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = s < nseg;  // no early return: the warp votes below need every lane
+    const xyzz_t* bk = buckets + (size_t)g * B + (size_t)(live ? s : 0) * BR_PER1;
     xyzz_t run = xyzz_identity(), acc = xyzz_identity();
 #pragma unroll 1
-    for (uint32_t d = per; d-- > 0;) {
-        xyzz_t q = ld_xyzz(bk + lo + d);
+    for (uint32_t d = BR_PER1; d-- > 0;) {
+        xyzz_t q = xyzz_identity();
+        if (live) q = ld_xyzz(bk + d);
         // sparse bucket sets (small scalars): skip the adds a whole warp does not need
         if (!__all_sync(0xffffffffu, xyzz_is_identity(q))) xyzz_add_ls(run, q);
         if (!__all_sync(0xffffffffu, xyzz_is_identity(run))) xyzz_add_ls(acc, run);
     }
-    // inclusive suffix scan of S_t (Hillis-Steele)
+    if (live) {
+        st_xyzz(S1 + (size_t)g * nseg + s, run);
+        st_xyzz(A1 + (size_t)g * nseg + s, acc);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_br_level2(const xyzz_t* __restrict__ S1, const xyzz_t* __restrict__ A1, uint32_t nseg, uint32_t nu, uint32_t total, xyzz_t* __restrict__ L2) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < total;  // total = G * nu
+    const uint32_t g = live ? t / nu : 0, u = live ? t % nu : 0;
+    const xyzz_t* s1 = S1 + (size_t)g * nseg + (size_t)u * BR_PER2;
+    const xyzz_t* a1 = A1 + (size_t)g * nseg + (size_t)u * BR_PER2;
+    xyzz_t run = xyzz_identity(), acc = xyzz_identity(), plain = xyzz_identity();
+#pragma unroll 1
+    for (uint32_t d = BR_PER2; d-- > 0;) {
+        xyzz_t q = xyzz_identity(), a = xyzz_identity();
+        if (live) {
+            q = ld_xyzz(s1 + d);
+            a = ld_xyzz(a1 + d);
+        }
+        // weight d (zero based): the running sum is added before this element joins it
+        if (!__all_sync(0xffffffffu, xyzz_is_identity(run))) xyzz_add_ls(acc, run);
+        if (!__all_sync(0xffffffffu, xyzz_is_identity(q))) xyzz_add_ls(run, q);
+        if (!__all_sync(0xffffffffu, xyzz_is_identity(a))) xyzz_add_ls(plain, a);
+    }
+    if (live) {
+        xyzz_t* o = L2 + (size_t)t * 3;
+        st_xyzz(o, run);
+        st_xyzz(o + 1, acc);
+        st_xyzz(o + 2, plain);
+    }
+}
+
+__device__ __forceinline__ xyzz_t block_tree_sum(xyzz_t v, xyzz_t* sm, uint32_t tid) {
+    __syncthreads();
+    sm[tid] = v;
+    __syncthreads();
+    for (uint32_t s = BR_T3 / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            xyzz_t a = sm[tid], b = sm[tid + s];
+            xyzz_add_ls(a, b);
+            sm[tid] = a;
+        }
+        __syncthreads();
+    }
+    return sm[0];
+}
+
+__global__ void __launch_bounds__(BR_T3)
+k_br_level3(const xyzz_t* __restrict__ L2, uint32_t nu, affine_t* __restrict__ out) {
+    __shared__ uint4 smem_raw[BR_T3 * sizeof(xyzz_t) / sizeof(uint4)];
+    xyzz_t* sm = reinterpret_cast<xyzz_t*>(smem_raw);
+    const uint32_t g = blockIdx.x, tid = threadIdx.x;
+    xyzz_t s2 = xyzz_identity(), a2 = xyzz_identity(), p1 = xyzz_identity();
+    if (tid < nu) {
+        const xyzz_t* in = L2 + ((size_t)g * nu + tid) * 3;
+        s2 = ld_xyzz(in);
+        a2 = ld_xyzz(in + 1);
+        p1 = ld_xyzz(in + 2);
+    }
+    // inclusive suffix scan of S2 (Hillis-Steele): T_u = sum_{v >= u} S2_v ;  sum_u u S2_u = sum_{u >= 1} T_u
+    xyzz_t run = s2;
     sm[tid] = run;
     __syncthreads();
 #pragma unroll 1
-    for (uint32_t d = 1; d < BR_THREADS; d <<= 1) {
+    for (uint32_t d = 1; d < BR_T3; d <<= 1) {
         xyzz_t o = xyzz_identity();
-        if (tid + d < BR_THREADS) o = sm[tid + d];
+        if (tid + d < BR_T3) o = sm[tid + d];
         __syncthreads();
         xyzz_add_ls(run, o);
         sm[tid] = run;
         __syncthreads();
     }
-    // run = T_tid.  tree-sum of T_t (t >= 1), then of A_t
-    xyzz_t total_s = sm[0];
-    __syncthreads();
-    if (tid == 0) sm[0] = xyzz_identity();
-    __syncthreads();
-    for (uint32_t s = BR_THREADS / 2; s > 0; s >>= 1) {
-        if (tid < s) {
-            xyzz_t a = sm[tid], b = sm[tid + s];
-            xyzz_add_ls(a, b);
-            sm[tid] = a;
-        }
-        __syncthreads();
-    }
-    xyzz_t w = sm[0];  // sum_t t * S_t
-    __syncthreads();
-    sm[tid] = acc;
-    __syncthreads();
-    for (uint32_t s = BR_THREADS / 2; s > 0; s >>= 1) {
-        if (tid < s) {
-            xyzz_t a = sm[tid], b = sm[tid + s];
-            xyzz_add_ls(a, b);
-            sm[tid] = a;
-        }
-        __syncthreads();
-    }
+    if (tid == 0) run = xyzz_identity();
+    const xyzz_t w = block_tree_sum(run, sm, tid);
+    const xyzz_t sa = block_tree_sum(a2, sm, tid);
+    const xyzz_t sp = block_tree_sum(p1, sm, tid);
     if (tid == 0) {
-        xyzz_t r = sm[0];
-        for (uint32_t i = 0; i < log_per; i++) w = xyzz_double(w);  // per * sum t S_t
-        xyzz_add(r, w);
-        if (base != 0 && !xyzz_is_identity(total_s)) {
-            xyzz_t tmp = xyzz_identity();
-            for (int bit = 31 - __clz(base); bit >= 0; bit--) {
-                tmp = xyzz_double(tmp);
-                if ((base >> bit) & 1u) xyzz_add(tmp, total_s);
-            }
-            xyzz_add(r, tmp);
-        }
-        st_xyzz(block_out + (size_t)g * nblk + blk, r);
+        xyzz_t r = w;
+        for (int i = 0; i < 3; i++) r = xyzz_double(r);  // BR_PER2 = 8
+        xyzz_add(r, sa);
+        for (int i = 0; i < 5; i++) r = xyzz_double(r);  // BR_PER1 = 32
+        xyzz_add(r, sp);
+        out[g] = xyzz_to_affine(r);
     }
-}
-
-__global__ void __launch_bounds__(32) k_final(const xyzz_t* __restrict__ block_out, uint32_t nblk, affine_t* out) {
-    __shared__ xyzz_t sm[32];
-    uint32_t g = blockIdx.x, lane = threadIdx.x;
-    xyzz_t acc = xyzz_identity();
-    for (uint32_t i = lane; i < nblk; i += 32) {
-        xyzz_t q = ld_xyzz(block_out + (size_t)g * nblk + i);
-        xyzz_add(acc, q);
-    }
-    sm[lane] = acc;
-    __syncwarp();
-    for (uint32_t s = 16; s > 0; s >>= 1) {
-        if (lane < s) {
-            xyzz_t a = sm[lane], b = sm[lane + s];
-            xyzz_add(a, b);
-            sm[lane] = a;
-        }
-        __syncwarp();
-    }
-    if (lane == 0) out[g] = xyzz_to_affine(sm[0]);
 }
 
 static uint32_t pick_window(size_t n) {
@@ -440,11 +457,8 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     const size_t slotsA = 2 * (size_t)nch1;
     const uint32_t nch2 = (uint32_t)((slotsA + L2 - 1) / L2);
     const size_t slotsB = 2 * (size_t)nch2;
-    uint32_t log_per = 0;
-    while (log_per < 5 && ((uint32_t)BR_THREADS << (log_per + 1)) <= B) log_per++;
-    const uint32_t per = 1u << log_per;
-    if (B % (BR_THREADS * per)) return fail(ctx, B2R_ERR_INVALID, "msm: bucket count not a multiple of the reduce tile");
-    const uint32_t nblk = B / (BR_THREADS * per);
+    if (B % (BR_PER1 * BR_PER2) || B / (BR_PER1 * BR_PER2) > BR_T3) return fail(ctx, B2R_ERR_INVALID, "msm: bucket count does not fit the reduce tiles");
+    const uint32_t nseg = B / BR_PER1, nu = nseg / BR_PER2;
 
     // carve the work arena
     size_t o = 0;
@@ -454,7 +468,7 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     size_t o_bk = carve(G * B * sizeof(xyzz_t));
     size_t o_ka = carve(G * slotsA * 4), o_pa = carve(G * slotsA * sizeof(xyzz_t));
     size_t o_kb = carve(G * slotsB * 4), o_pb = carve(G * slotsB * sizeof(xyzz_t));
-    size_t o_blk = carve(G * nblk * sizeof(xyzz_t));
+    size_t o_s1 = carve(G * nseg * sizeof(xyzz_t)), o_a1 = carve(G * nseg * sizeof(xyzz_t)), o_l2 = carve(G * nu * 3 * sizeof(xyzz_t));
     char* base = nullptr;
     B2R_TRY(scratch_get(ctx, SC_MSM_A, o, (void**)&base));
     uint32_t* cnt = (uint32_t*)(base + o_cnt);
@@ -467,7 +481,9 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     xyzz_t* pa = (xyzz_t*)(base + o_pa);
     uint32_t* kb = (uint32_t*)(base + o_kb);
     xyzz_t* pb = (xyzz_t*)(base + o_pb);
-    xyzz_t* blk = (xyzz_t*)(base + o_blk);
+    xyzz_t* s1 = (xyzz_t*)(base + o_s1);
+    xyzz_t* a1 = (xyzz_t*)(base + o_a1);
+    xyzz_t* l2 = (xyzz_t*)(base + o_l2);
     cudaStream_t st = ctx->stream;
 
     B2R_CUDA(ctx, cudaMemsetAsync(cnt, 0, G * B * 4, st));
@@ -508,10 +524,13 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
         to_b = !to_b;
     }
     { KTimer kt(ctx, "msm_bucket_reduce");
-    k_bucket_reduce<<<dim3(nblk, (unsigned)G), BR_THREADS, 0, st>>>(bk, B, per, log_per, blk, nblk); }
+    k_br_level1<<<dim3((nseg + 127) / 128, (unsigned)G), 128, 0, st>>>(bk, B, nseg, s1, a1);
+    B2R_LAUNCH_CHECK(ctx);
+    const uint32_t total = (uint32_t)(G * nu);
+    k_br_level2<<<(total + 127) / 128, 128, 0, st>>>(s1, a1, nseg, nu, total, l2); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_final");
-    k_final<<<(unsigned)G, 32, 0, st>>>(blk, nblk, out_dev); }
+    k_br_level3<<<(unsigned)G, BR_T3, 0, st>>>(l2, nu, out_dev); }
     B2R_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -520,7 +539,7 @@ static size_t msm_group_bytes(const b2r_bases* bs, size_t n) {
     const uint32_t W = bs->W, B = 1u << (bs->c - 1);
     size_t ent_cap = n * W;
     size_t nch1 = (ent_cap + 31) / 32, slotsA = 2 * nch1, slotsB = 2 * ((slotsA + 15) / 16);
-    return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + 4096 * 8;
+    return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + ((size_t)B / 16 + (size_t)B / 64 + 8) * 128 + 4096 * 8;
 }
 
 int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev) {
@@ -530,7 +549,7 @@ int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev
         return 0;
     }
     size_t per_vec = msm_group_bytes(bs, n);
-    size_t budget = (size_t)4 << 30;
+    size_t budget = (size_t)12 << 30;  // work arena per group of vectors (fewer, larger launches: 180 GB of HBM)
     size_t G = budget / per_vec;
     if (G < 1) G = 1;
     if (G > 1024) G = 1024;
