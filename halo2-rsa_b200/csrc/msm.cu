@@ -113,62 +113,86 @@ __global__ void k_precompute(const affine_t* __restrict__ bases, affine_t* __res
 }
 
 // ---- digits -----------------------------------------------------------------------------
-// signed window j of canonical scalar k: digit in (-2^(c-1), 2^(c-1)]
-struct DigitIter {
-    uint32_t k[9];
-    uint32_t carry;
-    __device__ __forceinline__ void init(const fe_t& canon) {
-        for (int i = 0; i < 8; i++) k[i] = canon.l[i];
-        k[8] = 0;
-        carry = 0;
+// signed window j of canonical scalar k: digit in (-2^(c-1), 2^(c-1)].  C is a template parameter and the window
+// loop is fully unrolled, so every word index and shift below is a compile-time constant (the first version indexed
+// the limb array at run time: k_digits was alu-pipe bound at 80 %, profiles/r01_ncu_prover.md).
+template <int C, int J>
+__device__ __forceinline__ int32_t signed_digit(const fe_t& k, uint32_t& carry) {
+    constexpr uint32_t bit = (uint32_t)J * C, w = bit >> 5, s = bit & 31;
+    uint32_t raw = 0;
+    if (w < 8) {
+        raw = k.l[w] >> s;
+        if (s + C > 32 && w + 1 < 8) raw |= k.l[w + 1] << (32 - s);
     }
-    // returns signed digit of window j (must be called with j = 0, 1, 2, ... in order)
-    __device__ __forceinline__ int32_t next(uint32_t j, uint32_t c) {
-        uint32_t bit = j * c, w = bit >> 5, s = bit & 31;
-        uint64_t two = (uint64_t)k[w] | ((uint64_t)(w + 1 <= 8 ? k[w + 1] : 0) << 32);
-        uint32_t raw = (uint32_t)((two >> s) & ((1u << c) - 1)) + carry;
-        if (raw > (1u << (c - 1))) {
-            carry = 1;
-            return (int32_t)raw - (int32_t)(1u << c);
-        }
-        carry = 0;
-        return (int32_t)raw;
+    raw = (raw & ((1u << C) - 1)) + carry;
+    if (raw > (1u << (C - 1))) {
+        carry = 1;
+        return (int32_t)raw - (int32_t)(1u << C);
     }
-};
+    carry = 0;
+    return (int32_t)raw;
+}
 
 template <bool SCATTER>
+__device__ __forceinline__ void digit_emit(int32_t d, bool live, uint32_t j, uint32_t i, uint32_t n_table, uint32_t lane, uint32_t* cnt,
+                                           uint32_t* ent, uint32_t* key) {
+    const bool has = live && d != 0;
+    const uint32_t b = has ? (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
+    // warp-aggregate lanes that hit the same bucket
+    const uint32_t act = __ballot_sync(0xffffffffu, has);
+    if (has) {
+        const uint32_t peers = __match_any_sync(act, b);
+        const uint32_t leader = __ffs(peers) - 1;
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&cnt[b], __popc(peers));
+        if (SCATTER) {
+            base = __shfl_sync(peers, base, leader);
+            ent[base + rank] = (j * n_table + i) | (d < 0 ? 0x80000000u : 0u);
+            key[base + rank] = b;
+        }
+    }
+}
+
+template <bool SCATTER, int C, int J, int W>
+struct DigitLoop {
+    static __device__ __forceinline__ void run(const fe_t& k, uint32_t& carry, bool live, uint32_t i, uint32_t n_table, uint32_t lane,
+                                               uint32_t* cnt, uint32_t* ent, uint32_t* key) {
+        const int32_t d = signed_digit<C, J>(k, carry);
+        digit_emit<SCATTER>(d, live, J, i, n_table, lane, cnt, ent, key);
+        DigitLoop<SCATTER, C, J + 1, W>::run(k, carry, live, i, n_table, lane, cnt, ent, key);
+    }
+};
+template <bool SCATTER, int C, int W>
+struct DigitLoop<SCATTER, C, W, W> {
+    static __device__ __forceinline__ void run(const fe_t&, uint32_t&, bool, uint32_t, uint32_t, uint32_t, uint32_t*, uint32_t*, uint32_t*) {}
+};
+
+template <bool SCATTER, int C>
 __global__ void __launch_bounds__(256)
-k_digits(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_t c, uint32_t W, uint32_t B,
+k_digits(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_t B,
          uint32_t* counts /*[G][B] (count) or cursor (scatter)*/, uint32_t* entries, uint32_t* keys, size_t ent_stride) {
+    constexpr int W = (255 + C - 1) / C;
     uint32_t g = blockIdx.y;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
     fe_t s = Fr::zero();
     if (live) s = Fr::from_mont(ldg_fe(scalars + (size_t)g * n + i));
-    DigitIter it;
-    it.init(s);
     uint32_t* cnt = counts + (size_t)g * B;
     uint32_t* ent = SCATTER ? entries + (size_t)g * ent_stride : nullptr;
     uint32_t* key = SCATTER ? keys + (size_t)g * ent_stride : nullptr;
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t j = 0; j < W; j++) {
-        int32_t d = it.next(j, c);
-        bool has = live && d != 0;
-        uint32_t b = has ? (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
-        // warp-aggregate lanes that hit the same bucket
-        uint32_t act = __ballot_sync(0xffffffffu, has);
-        if (has) {
-            uint32_t peers = __match_any_sync(act, b);
-            uint32_t leader = __ffs(peers) - 1;
-            uint32_t rank = __popc(peers & ((1u << lane) - 1));
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(&cnt[b], __popc(peers));
-            if (SCATTER) {
-                base = __shfl_sync(peers, base, leader);
-                ent[base + rank] = (j * n_table + i) | (d < 0 ? 0x80000000u : 0u);
-                key[base + rank] = b;
-            }
-        }
+    uint32_t carry = 0;
+    DigitLoop<SCATTER, C, 0, W>::run(s, carry, live, i, n_table, lane, cnt, ent, key);
+}
+
+template <bool SCATTER>
+static void launch_digits(uint32_t c, dim3 grid, cudaStream_t st, const fe_t* scalars, uint32_t n, uint32_t n_table, uint32_t B, uint32_t* counts,
+                          uint32_t* entries, uint32_t* keys, size_t ent_stride) {
+    switch (c) {
+        case 10: k_digits<SCATTER, 10><<<grid, 256, 0, st>>>(scalars, n, n_table, B, counts, entries, keys, ent_stride); break;
+        case 13: k_digits<SCATTER, 13><<<grid, 256, 0, st>>>(scalars, n, n_table, B, counts, entries, keys, ent_stride); break;
+        default: k_digits<SCATTER, 16><<<grid, 256, 0, st>>>(scalars, n, n_table, B, counts, entries, keys, ent_stride); break;
     }
 }
 
@@ -340,7 +364,7 @@ k_accum_slots(const uint32_t* __restrict__ in_keys, const xyzz_t* __restrict__ i
 //   result = P1 + 32 (A2 + 8 W), one inversion to affine.
 static constexpr uint32_t BR_PER1 = 32, BR_PER2 = 8, BR_T3 = 128;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 k_br_level1(const xyzz_t* __restrict__ buckets, uint32_t B, uint32_t nseg, xyzz_t* __restrict__ S1, xyzz_t* __restrict__ A1) {
     const uint32_t g = blockIdx.y, s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < nseg;  // no early return: the warp votes below need every lane
@@ -350,7 +374,8 @@ k_br_level1(const xyzz_t* __restrict__ buckets, uint32_t B, uint32_t nseg, xyzz_
     for (uint32_t d = BR_PER1; d-- > 0;) {
         xyzz_t q = xyzz_identity();
         if (live) q = ld_xyzz(bk + d);
-        // sparse bucket sets (small scalars): skip the adds a whole warp does not need
+        // sparse bucket sets (small scalars): skip the adds a whole warp does not need.  (Issuing acc += run and
+        // run += q as two independent additions per step was measured slower: 61 vs 47 ms per 64-proof step.)
         if (!__all_sync(0xffffffffu, xyzz_is_identity(q))) xyzz_add_ls(run, q);
         if (!__all_sync(0xffffffffu, xyzz_is_identity(run))) xyzz_add_ls(acc, run);
     }
@@ -490,13 +515,13 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     B2R_CUDA(ctx, cudaMemsetAsync(bk, 0, G * B * sizeof(xyzz_t), st));
     dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
     { KTimer kt(ctx, "msm_count", (double)G * n);
-    k_digits<false><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cnt, nullptr, nullptr, 0); }
+    launch_digits<false>(c, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cnt, nullptr, nullptr, 0); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_scan");
     k_scan<<<(unsigned)G, 1024, 0, st>>>(cnt, off, cur, B); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_scatter", (double)G * n);
-    k_digits<true><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, c, W, B, cur, ent, key, ent_cap); }
+    launch_digits<true>(c, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cur, ent, key, ent_cap); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_accum_entries", (double)G * n);
     k_accum_entries<L1><<<dim3((nch1 + 127) / 128, (unsigned)G), 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa,

@@ -400,7 +400,7 @@ struct QuotArgs {
     fe_t* h;              // [QB][ext_n]
     uint32_t ext_n, step, QB;
 };
-__global__ void __launch_bounds__(128) k_quotient(const QuotArgs A, const DevConsts C) {
+__global__ void __launch_bounds__(128, 3) k_quotient(const QuotArgs A, const DevConsts C) {
     const uint32_t q = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
     if (i >= A.ext_n) return;
     const uint32_t mask = A.ext_n - 1, nx = (i + A.step) & mask, pv = (i - A.step) & mask, lastr = (i - (BF + 1) * A.step) & mask;
