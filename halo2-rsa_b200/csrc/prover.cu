@@ -397,42 +397,51 @@ struct QuotArgs {
     const fe_t* l_c;      // [3][ext_n]
     const fe_t* tw_ext;   // omega_ext^e, e < ext_n / 2
     const fe_t* chal;     // [QB][8] (already offset to the sub-batch)
+    const fe_t* ypow;     // [QB][NCONS]: y^(NCONS - 1 - k) for constraint k (already offset to the sub-batch)
     fe_t* h;              // [QB][ext_n]
     uint32_t ext_n, step, QB;
 };
+// constraints in halo2's order: gate, 3 permutation boundary terms, NSETS product terms, 5 per lookup
+static constexpr int NCONS = 1 + 3 + NSETS + 5 * NLOOK;
+static_assert(NSETS == 2, "constraint numbering below assumes two permutation sets");
+// h = sum_k C_k y^(NCONS-1-k) / (X^n - 1).  halo2 folds the constraints by Horner in y (two products per constraint);
+// every C_k here is l(X) * e_k with l one of {1, l0, l_last, l_active}, so the sum is regrouped as
+// gate y^30 + l0 sum(e_k y^..) + l_last sum(..) + l_active sum(..): one product per constraint plus three.
 __global__ void __launch_bounds__(128, 3) k_quotient(const QuotArgs A, const DevConsts C) {
     const uint32_t q = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
     if (i >= A.ext_n) return;
     const uint32_t mask = A.ext_n - 1, nx = (i + A.step) & mask, pv = (i - A.step) & mask, lastr = (i - (BF + 1) * A.step) & mask;
-    const fe_t theta = ldv(A.chal + (size_t)q * 8), beta = ldv(A.chal + (size_t)q * 8 + 1), gamma = ldv(A.chal + (size_t)q * 8 + 2),
-               y = ldv(A.chal + (size_t)q * 8 + 3);
+    const fe_t theta = ldv(A.chal + (size_t)q * 8), beta = ldv(A.chal + (size_t)q * 8 + 1), gamma = ldv(A.chal + (size_t)q * 8 + 2);
+    const fe_t* yp = A.ypow + (size_t)q * NCONS;
     auto ext = [&](int slot, uint32_t idx) { return ldv(A.E + ((size_t)slot * A.QB + q) * A.ext_n + idx); };
     auto fx = [&](int col) { return ldv_nc(A.fixed_c + (size_t)col * A.ext_n + i); };
+    auto wy = [&](const fe_t& e, int k) { return Fr::mul(e, ldv_nc(yp + k)); };
     fe_t col[NPERM];
     for (int c = 0; c < NADV; c++) col[c] = ext(SL_ADV + c, i);
     col[NADV] = Fr::zero();
     // main gate
-    fe_t acc = Fr::mul(col[0], fx(FX_SA));
-    acc = Fr::add(acc, Fr::mul(col[1], fx(FX_SB)));
-    acc = Fr::add(acc, Fr::mul(col[2], fx(FX_SC)));
-    acc = Fr::add(acc, Fr::mul(col[3], fx(FX_SD)));
-    acc = Fr::add(acc, Fr::mul(col[4], fx(FX_SE)));
-    acc = Fr::add(acc, Fr::mul(Fr::mul(col[0], col[1]), fx(FX_MUL_AB)));
-    acc = Fr::add(acc, Fr::mul(Fr::mul(col[2], col[3]), fx(FX_MUL_CD)));
-    acc = Fr::add(acc, Fr::mul(ext(SL_ADV + 4, nx), fx(FX_SE_NEXT)));
-    acc = Fr::add(acc, fx(FX_CONST));
-    const fe_t l0 = ldv_nc(A.l_c + i), l_last = ldv_nc(A.l_c + (size_t)A.ext_n + i), l_active = ldv_nc(A.l_c + 2 * (size_t)A.ext_n + i);
+    fe_t gate = Fr::mul(col[0], fx(FX_SA));
+    gate = Fr::add(gate, Fr::mul(col[1], fx(FX_SB)));
+    gate = Fr::add(gate, Fr::mul(col[2], fx(FX_SC)));
+    gate = Fr::add(gate, Fr::mul(col[3], fx(FX_SD)));
+    gate = Fr::add(gate, Fr::mul(col[4], fx(FX_SE)));
+    gate = Fr::add(gate, Fr::mul(Fr::mul(col[0], col[1]), fx(FX_MUL_AB)));
+    gate = Fr::add(gate, Fr::mul(Fr::mul(col[2], col[3]), fx(FX_MUL_CD)));
+    gate = Fr::add(gate, Fr::mul(ext(SL_ADV + 4, nx), fx(FX_SE_NEXT)));
+    gate = Fr::add(gate, fx(FX_CONST));
+    fe_t acc = wy(gate, 0);
     const fe_t one = Fr::one();
     // permutation argument
     fe_t pz[NSETS];
     for (int s = 0; s < NSETS; s++) pz[s] = ext(SL_PZ + s, i);
-    acc = Fr::add(Fr::mul(acc, y), Fr::mul(l0, Fr::sub(one, pz[0])));
-    acc = Fr::add(Fr::mul(acc, y), Fr::mul(l_last, Fr::sub(Fr::sqr(pz[NSETS - 1]), pz[NSETS - 1])));
-    for (int s = 1; s < NSETS; s++) acc = Fr::add(Fr::mul(acc, y), Fr::mul(l0, Fr::sub(pz[s], ext(SL_PZ + s - 1, lastr))));
+    fe_t g0 = wy(Fr::sub(one, pz[0]), 1);                                                   // l0 group
+    fe_t glast = wy(Fr::sub(Fr::sqr(pz[NSETS - 1]), pz[NSETS - 1]), 2);                     // l_last group
+    g0 = Fr::add(g0, wy(Fr::sub(pz[1], ext(SL_PZ, lastr)), 3));
     // X at this point of the coset: zeta * omega_ext^i
     const uint32_t half = A.ext_n >> 1;
     fe_t xi = i < half ? ldv_nc(A.tw_ext + i) : Fr::neg(ldv_nc(A.tw_ext + (i - half)));
     const fe_t beta_x = Fr::mul(beta, Fr::mul(xi, C.zeta));
+    fe_t gact = Fr::zero();                                                                 // l_active group
     for (int s = 0; s < NSETS; s++) {
         fe_t left = ext(SL_PZ + s, nx), right = pz[s];
         for (int c = s * CHUNK; c < (s + 1) * CHUNK && c < NPERM; c++) {
@@ -440,7 +449,7 @@ __global__ void __launch_bounds__(128, 3) k_quotient(const QuotArgs A, const Dev
             left = Fr::mul(left, Fr::add(Fr::mul(beta, ldv_nc(A.sigma_c + (size_t)c * A.ext_n + i)), vg));
             right = Fr::mul(right, Fr::add(Fr::mul(beta_x, C.delta_pows[c]), vg));
         }
-        acc = Fr::add(Fr::mul(acc, y), Fr::mul(l_active, Fr::sub(left, right)));
+        gact = Fr::add(gact, wy(Fr::sub(left, right), 4 + s));
     }
     // lookup arguments
     const fe_t tbl_g = Fr::add(Fr::add(Fr::mul(fx(FX_T_TAG), theta), fx(FX_T_VALUE)), gamma);
@@ -448,18 +457,22 @@ __global__ void __launch_bounds__(128, 3) k_quotient(const QuotArgs A, const Dev
     const fe_t s_c = fx(FX_S_COMP), s_o = fx(FX_S_OVER);
 #pragma unroll 1
     for (int l = 0; l < NLOOK; l++) {
+        const int k0 = 4 + NSETS + 5 * l;
         const fe_t z = ext(SL_LZ + l, i), zn = ext(SL_LZ + l, nx), ap = ext(SL_LA + 2 * l, i), sp = ext(SL_LA + 2 * l + 1, i),
                    apv = ext(SL_LA + 2 * l, pv);
         const fe_t inp = l < 4 ? Fr::add(tag_c, Fr::mul(s_c, col[l])) : Fr::add(tag_o, Fr::mul(s_o, col[0]));
-        acc = Fr::add(Fr::mul(acc, y), Fr::mul(l0, Fr::sub(one, z)));
-        acc = Fr::add(Fr::mul(acc, y), Fr::mul(l_last, Fr::sub(Fr::sqr(z), z)));
+        g0 = Fr::add(g0, wy(Fr::sub(one, z), k0));
+        glast = Fr::add(glast, wy(Fr::sub(Fr::sqr(z), z), k0 + 1));
         const fe_t left = Fr::mul(Fr::mul(zn, Fr::add(ap, beta)), Fr::add(sp, gamma));
         const fe_t right = Fr::mul(Fr::mul(z, Fr::add(inp, beta)), tbl_g);
-        acc = Fr::add(Fr::mul(acc, y), Fr::mul(l_active, Fr::sub(left, right)));
+        gact = Fr::add(gact, wy(Fr::sub(left, right), k0 + 2));
         const fe_t d = Fr::sub(ap, sp);
-        acc = Fr::add(Fr::mul(acc, y), Fr::mul(l0, d));
-        acc = Fr::add(Fr::mul(acc, y), Fr::mul(l_active, Fr::mul(d, Fr::sub(ap, apv))));
+        g0 = Fr::add(g0, wy(d, k0 + 3));
+        gact = Fr::add(gact, wy(Fr::mul(d, Fr::sub(ap, apv)), k0 + 4));
     }
+    acc = Fr::add(acc, Fr::mul(ldv_nc(A.l_c + i), g0));
+    acc = Fr::add(acc, Fr::mul(ldv_nc(A.l_c + (size_t)A.ext_n + i), glast));
+    acc = Fr::add(acc, Fr::mul(ldv_nc(A.l_c + 2 * (size_t)A.ext_n + i), gact));
     stv(A.h + (size_t)q * A.ext_n + i, Fr::mul(acc, C.t_inv[i & (A.step - 1)]));
 }
 
@@ -815,7 +828,7 @@ int32_t b2r_pk_export_vk(const b2r_pk* pk, b2r_g1_affine* fixed_commitments, b2r
 namespace b2r {
 
 struct ProveScratch {
-    fe_t *P, *hbuf, *num, *den, *pref, *chunk_prod, *E, *hext, *lc, *wq, *sorted_cv, *chal, *points, *scal, *evals;
+    fe_t *P, *hbuf, *num, *den, *pref, *chunk_prod, *E, *hext, *lc, *wq, *sorted_cv, *chal, *ypow, *points, *scal, *evals;
     uint32_t *hist, *order, *err;
     LookupPlan* plans;
     affine_t* cm;
@@ -878,7 +891,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     const size_t oCp = carve((size_t)NZ * B * nch * 32);
     const size_t oE = carve((size_t)NTRANS * QB * ext_n * 32), oHext = carve((size_t)QB * ext_n * 32);
     const size_t oLc = carve((size_t)B * NPOINTS * n * 32), oWq = carve((size_t)B * NPOINTS * n * 32);
-    const size_t oCv = carve((size_t)B * MAX_TABLE * 32), oChal = carve((size_t)B * 8 * 32), oPts = carve((size_t)B * NPOINTS * 32);
+    const size_t oCv = carve((size_t)B * MAX_TABLE * 32), oChal = carve((size_t)B * 8 * 32), oYp = carve((size_t)B * NCONS * 32), oPts = carve((size_t)B * NPOINTS * 32);
     const size_t oScal = carve((size_t)B * NPOINTS * MAXTERMS * 32), oEv = carve((size_t)B * NEVAL * 32);
     const size_t oHist = carve((size_t)B * NLOOK * MAX_TABLE * 4), oOrd = carve((size_t)B * MAX_TABLE * 4), oErr = carve((size_t)B * 4);
     const size_t oPlans = carve((size_t)B * NLOOK * sizeof(LookupPlan));
@@ -890,7 +903,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     ProveScratch S;
     S.P = (fe_t*)(base + oP); S.hbuf = (fe_t*)(base + oH); S.num = (fe_t*)(base + oNum); S.den = (fe_t*)(base + oDen);
     S.pref = (fe_t*)(base + oPref); S.chunk_prod = (fe_t*)(base + oCp); S.E = (fe_t*)(base + oE); S.hext = (fe_t*)(base + oHext);
-    S.lc = (fe_t*)(base + oLc); S.wq = (fe_t*)(base + oWq); S.sorted_cv = (fe_t*)(base + oCv); S.chal = (fe_t*)(base + oChal);
+    S.lc = (fe_t*)(base + oLc); S.wq = (fe_t*)(base + oWq); S.sorted_cv = (fe_t*)(base + oCv); S.chal = (fe_t*)(base + oChal); S.ypow = (fe_t*)(base + oYp);
     S.points = (fe_t*)(base + oPts); S.scal = (fe_t*)(base + oScal); S.evals = (fe_t*)(base + oEv);
     S.hist = (uint32_t*)(base + oHist); S.order = (uint32_t*)(base + oOrd); S.err = (uint32_t*)(base + oErr);
     S.plans = (LookupPlan*)(base + oPlans); S.cm = (affine_t*)(base + oCm); S.eplan = (EvalPlan*)(base + oEp);
@@ -907,7 +920,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     B2R_CUDA(ctx, cudaMemsetAsync(S.err, 0, (size_t)B * 4, st));
 
     std::vector<Transcript> tr(B);
-    std::vector<fe_t> chal((size_t)B * 8, Fr::zero());
+    std::vector<fe_t> chal((size_t)B * 8, Fr::zero()), ypow((size_t)B * NCONS);
     std::vector<affine_t> cm((size_t)B * 16);
     std::vector<uint8_t> valid(B);
     std::vector<uint32_t> err(B);
@@ -984,8 +997,12 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     for (uint32_t p = 0; p < B; p++) {
         for (int j = 0; j < NZ + 1; j++) tr[p].write_point(cm[(size_t)j * B + p].x, cm[(size_t)j * B + p].y);
         chal[(size_t)p * 8 + 3] = tr[p].squeeze();  // y
+        fe_t* yp = ypow.data() + (size_t)p * NCONS;   // y^(NCONS-1-k): the weight of constraint k in h
+        yp[NCONS - 1] = Fr::one();
+        for (int k = NCONS - 2; k >= 0; k--) yp[k] = Fr::mul(yp[k + 1], chal[(size_t)p * 8 + 3]);
     }
     B2R_TRY(push_chal());
+    B2R_CUDA(ctx, cudaMemcpyAsync(S.ypow, ypow.data(), ypow.size() * 32, cudaMemcpyHostToDevice, st));
     // ---- phase 4: coefficient forms, extended coset, quotient
     B2R_TRY(b2r_intt_fr_batch_dev(ctx, (b2r_fr*)S.P, (size_t)NTRANS * B, k));
     for (uint32_t q0 = 0; q0 < B; q0 += QB) {
@@ -994,7 +1011,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
             B2R_TRY(b2r_coset_ntt_fr_batch_dev(ctx, (b2r_fr*)(S.P + ((size_t)s * B + q0) * n), qb, k, pk->ext_k, (b2r_fr*)(S.E + (size_t)s * QB * ext_n)));
         QuotArgs A;
         A.E = S.E; A.fixed_c = pk->fixed_cosets; A.sigma_c = pk->sigma_cosets; A.l_c = pk->l_cosets; A.tw_ext = tw_ext;
-        A.chal = S.chal + (size_t)q0 * 8; A.h = S.hext; A.ext_n = ext_n; A.step = ext_n / n; A.QB = QB;
+        A.chal = S.chal + (size_t)q0 * 8; A.ypow = S.ypow + (size_t)q0 * NCONS; A.h = S.hext; A.ext_n = ext_n; A.step = ext_n / n; A.QB = QB;
         { KTimer kt(ctx, "quotient", (double)qb);
         k_quotient<<<dim3(ext_n / 128, qb), 128, 0, st>>>(A, C); }
         B2R_LAUNCH_CHECK(ctx);
