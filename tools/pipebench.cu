@@ -5,7 +5,9 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "experiments/ec29.cuh"
+#include "experiments/field_f64.cuh"
 
 using namespace b2r;
 
@@ -192,6 +194,22 @@ __global__ void __launch_bounds__(128, 4) k_madd_29(fe_t* out, const affine_t* p
     out[t] = Fq29::pack(Fq29::reduce(Fq29::add(Fq29::add(acc.x, acc.y), Fq29::add(acc.zz, acc.zzz))));
 }
 
+template <int ILP, bool SQR>
+__global__ void k_f64mul(fe_t* out, const fe_t* in, int iters) {
+    fe_t x[ILP], y;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    y = in[t & 1023];
+    for (int j = 0; j < ILP; j++) x[j] = in[(t + j + 1) & 1023];
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++) x[j] = SQR ? FqF64::sqr(x[j]) : FqF64::mul(x[j], y);
+    }
+    fe_t r = x[0];
+    for (int j = 1; j < ILP; j++) r = Fq::add(r, x[j]);
+    out[t] = r;
+}
+
 template <class F>
 static double time_ms(F launch, int reps = 5) {
     cudaEvent_t s, e;
@@ -236,6 +254,8 @@ int main(int argc, char** argv) {
         CK(cudaMemset(buf, 0x11, 1024 * 64));
         k_fqmul<1><<<grid, 256>>>(out0, in0, 512);
         k_f29mul<1, false><<<grid, 256>>>(out0, in0, 512);
+        k_f64mul<1, false><<<grid, 256>>>(out0, in0, 512);
+        k_f64mul<2, false><<<grid, 256>>>(out0, in0, 512);
         k_f29mul<2, true><<<grid, 256>>>(out0, in0, 512);
         k_madd_old<<<sms * 4, 128>>>(out0, (const affine_t*)buf, 256);
         k_madd_29<<<sms * 4, 128>>>(out0, (const affine_t*)buf, 256);
@@ -314,6 +334,40 @@ int main(int argc, char** argv) {
             double tn = time_ms([&] { k_madd_29<<<grid, 128>>>(out, pts, mi); });
             const double m = (double)grid * 128 * mi;
             printf("madd  warps/SM %2d  32-bit limbs %6.2f   29-bit limbs %6.2f  Gadd/s\n", cps * 4, m / to / 1e6, m / tn / 1e6);
+        }
+    }
+    {
+        // FP64-assisted product: parity with Fq::mul on the device, then throughput
+        CK(cudaMemset(buf, 0x11, 1024 * 64));
+        fe_t* i0 = (fe_t*)buf;
+        fe_t* o1 = i0 + 4096;
+        fe_t* o2 = o1 + (size_t)sms * 8 * 256;
+        const int grid = sms * 8;
+        // pseudo-random canonical inputs: repeated squaring of the 0x11.. pattern
+        k_fqmul<1><<<4, 256>>>(i0, i0, 3);
+        CK(cudaDeviceSynchronize());
+        k_fqmul<1><<<grid, 256>>>(o1, i0, 64);
+        k_f64mul<1, false><<<grid, 256>>>(o2, i0, 64);
+        CK(cudaDeviceSynchronize());
+        const size_t cnt = (size_t)grid * 256;
+        fe_t* h1 = (fe_t*)malloc(cnt * 32);
+        fe_t* h2 = (fe_t*)malloc(cnt * 32);
+        CK(cudaMemcpy(h1, o1, cnt * 32, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h2, o2, cnt * 32, cudaMemcpyDeviceToHost));
+        size_t bad = 0;
+        for (size_t i = 0; i < cnt; i++) bad += memcmp(&h1[i], &h2[i], 32) != 0;
+        printf("F64-assisted mul parity vs Fq::mul: %zu mismatches of %zu (64 chained products each)\n", bad, cnt);
+        free(h1); free(h2);
+        for (int th : {128, 256}) {
+            for (int cps : {1, 2, 3, 4, 6, 8}) {
+                const int g2 = sms * cps;
+                double t1 = time_ms([&] { k_f64mul<1, false><<<g2, th>>>(o2, i0, 512); });
+                double t2 = time_ms([&] { k_f64mul<2, false><<<g2, th>>>(o2, i0, 512); });
+                double s1 = time_ms([&] { k_f64mul<1, true><<<g2, th>>>(o2, i0, 512); });
+                const double m = (double)g2 * th * 512;
+                printf("F64::mul warps/SM %2d  ILP1 %6.1f  ILP2 %6.1f  Gmul/s   sqr ILP1 %6.1f Gsqr/s\n", cps * th / 32, m / t1 / 1e6, 2 * m / t2 / 1e6,
+                       m / s1 / 1e6);
+            }
         }
     }
     return 0;
