@@ -15,6 +15,8 @@
 // Scaling (1/n) and the coset ZETA-power twists are fused into the first load / last store.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "ctx.hpp"
 
 namespace b2r {
@@ -102,23 +104,49 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
     }
     __syncthreads();
 
-    // ---- S radix-2 stages in shared memory (decimation in frequency, in place)
+    // ---- S radix-2 stages in shared memory (decimation in frequency, in place), two stages per round trip: a thread
+    // takes rows r0, r0+q, r0+2q, r0+3q (q = a quarter of the current block), does the two butterflies of stage i and
+    // the two of stage i+1 in registers (4 twiddle products, as two radix-2 stages would) and writes the 4 rows back:
+    // half the shared-memory traffic and barriers of the plain radix-2 loop.
+    uint32_t i = 0;
 #pragma unroll 1
-    for (uint32_t i = 0; i < S; i++) {
-        const uint32_t log_half = S - 1 - i, half = 1u << log_half;
+    for (; i + 1 < S; i += 2) {
+        const uint32_t log_q = S - 2 - i, q = 1u << log_q;
+        for (uint32_t g = tid; g < ((R / 4) << log_c); g += T) {
+            const uint32_t c = g & cmask, gf = g >> log_c;
+            const uint32_t blk = gf >> log_q, rp = gf & (q - 1);
+            const uint32_t i0 = ((((blk << (log_q + 2)) + rp)) << log_c) + c, st = q << log_c;
+            const uint32_t base = ((c0 + c) >> A.log_s) << A.log_s;  // s * p'
+            const uint32_t ea = (base + (rp << log_cols)) << i;          // stage i, rows (r0, r0 + 2q)
+            const uint32_t eb = (base + ((rp + q) << log_cols)) << i;    // stage i, rows (r0 + q, r0 + 3q)
+            const uint32_t ec = ea << 1;                                 // stage i + 1, both pairs
+            const fe_t a0 = ld_fe(sm + i0), a1 = ld_fe(sm + i0 + st), a2 = ld_fe(sm + i0 + 2 * st), a3 = ld_fe(sm + i0 + 3 * st);
+            const fe_t u0 = Fr::add(a0, a2), u1 = Fr::add(a1, a3);
+            fe_t d0 = Fr::sub(a0, a2), d1 = Fr::sub(a1, a3);
+            if (ea) d0 = Fr::mul(d0, ld_fe_nc(A.tw + ea));
+            d1 = Fr::mul(d1, ld_fe_nc(A.tw + eb));
+            const fe_t wc = ld_fe_nc(A.tw + ec);
+            st_fe(sm + i0, Fr::add(u0, u1));
+            st_fe(sm + i0 + 2 * st, Fr::add(d0, d1));
+            fe_t v1 = Fr::sub(u0, u1), v3 = Fr::sub(d0, d1);
+            if (ec) {
+                v1 = Fr::mul(v1, wc);
+                v3 = Fr::mul(v3, wc);
+            }
+            st_fe(sm + i0 + st, v1);
+            st_fe(sm + i0 + 3 * st, v3);
+        }
+        __syncthreads();
+    }
+    if (i < S) {  // odd S: one radix-2 stage left (half = 1)
         for (uint32_t b = tid; b < ((R / 2) << log_c); b += T) {
-            uint32_t c = b & cmask, bf = b >> log_c;
-            uint32_t blk = bf >> log_half, rp = bf & (half - 1);
-            uint32_t i0 = (((blk << (log_half + 1)) + rp) << log_c) + c;
-            uint32_t i1 = i0 + (half << log_c);
-            uint32_t pp = (c0 + c) >> A.log_s;  // p'
-            // exponent of omega_n: s*2^i*(p' + (l/R)*r')
-            uint32_t e = ((pp << A.log_s) << i) + ((rp << log_cols) << i);
-            fe_t a = ld_fe(sm + i0), bb = ld_fe(sm + i1);
-            fe_t u = Fr::add(a, bb);
+            const uint32_t c = b & cmask, bf = b >> log_c;
+            const uint32_t i0 = ((bf << 1) << log_c) + c, i1 = i0 + (1u << log_c);
+            const uint32_t e = (((c0 + c) >> A.log_s) << A.log_s) << i;
+            const fe_t a = ld_fe(sm + i0), bb = ld_fe(sm + i1);
             fe_t d = Fr::sub(a, bb);
             if (e) d = Fr::mul(d, ld_fe_nc(A.tw + e));
-            st_fe(sm + i0, u);
+            st_fe(sm + i0, Fr::add(a, bb));
             st_fe(sm + i1, d);
         }
         __syncthreads();
@@ -301,7 +329,14 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
             A.post3[2] = Fr::mul(n_inv, zeta);
         }
         uint32_t log_cols = log_n - S[p];
-        uint32_t log_c = (S[p] >= 9) ? 2 : 3;
+        // columns per CTA: 256 threads want >= 256 four-row groups (2^(S-2) per column); measured best on B200
+        // (tools/microbench.py, B2R_NTT_LOGC sweep)
+        uint32_t log_c = (S[p] >= 8) ? 2 : (S[p] == 7 ? 3 : 4);
+        {   // tuning hook (tools/microbench.py): columns per CTA
+            static const char* ov = getenv("B2R_NTT_LOGC");
+            if (ov) log_c = (uint32_t)atoi(ov);
+            if ((((size_t)sizeof(fe_t) << S[p]) << log_c) > 200 * 1024) log_c = 2;
+        }
         if (log_c > log_cols) log_c = log_cols;
         if (p > 0 && log_c > log_s) log_c = log_s;
         A.log_c = log_c;
