@@ -35,6 +35,10 @@ struct b2r_bases {
 
 namespace b2r {
 
+// entries of the bucket-sorted list per thread of k_accum_entries (64: half the chunk-boundary partial sums of 32)
+#ifndef MSM_L1
+#define MSM_L1 64
+#endif
 static constexpr uint32_t SLOT_INVALID = 0xffffffffu;
 static constexpr uint32_t SLOT_BEGINS = 0x80000000u;
 static constexpr uint32_t SLOT_ENDS = 0x40000000u;
@@ -476,7 +480,7 @@ static uint32_t pick_window(size_t n) {
 
 static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t G, size_t n, affine_t* out_dev) {
     const uint32_t c = bs->c, W = bs->W, B = 1u << (c - 1);
-    constexpr uint32_t L1 = 32, L2 = 16;
+    constexpr uint32_t L1 = MSM_L1, L2 = 16;
     const size_t ent_cap = (size_t)n * W;
     const uint32_t nch1 = (uint32_t)((ent_cap + L1 - 1) / L1);
     const size_t slotsA = 2 * (size_t)nch1;
@@ -563,7 +567,7 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
 static size_t msm_group_bytes(const b2r_bases* bs, size_t n) {
     const uint32_t W = bs->W, B = 1u << (bs->c - 1);
     size_t ent_cap = n * W;
-    size_t nch1 = (ent_cap + 31) / 32, slotsA = 2 * nch1, slotsB = 2 * ((slotsA + 15) / 16);
+    size_t nch1 = (ent_cap + MSM_L1 - 1) / MSM_L1, slotsA = 2 * nch1, slotsB = 2 * ((slotsA + 15) / 16);
     return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + ((size_t)B / 16 + (size_t)B / 64 + 8) * 128 + 4096 * 8;
 }
 
