@@ -23,6 +23,8 @@
 // Algorithmic HBM bytes: 32 B per scalar + 64 B per gathered table point.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "ctx.hpp"
 #include "ec.cuh"
 
@@ -258,8 +260,8 @@ __device__ __forceinline__ void emit_run(uint32_t b, const xyzz_t& acc, bool beg
 // and walks them with ONE flat loop, so all lanes of a warp execute the same mixed add in the same
 // iteration whatever the bucket boundaries are (the nested run loops of the first version left 9.8
 // of 32 lanes active, profiles/r01_ncu_full_baseline.md).  A bucket change costs a predicated flush.
-template <int L>
-__global__ void __launch_bounds__(128, 4)
+template <int L, int MINB, bool PF>
+__global__ void __launch_bounds__(128, MINB)
 k_accum_entries(const affine_t* __restrict__ table, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ keys,
                 size_t ent_stride, const uint32_t* __restrict__ offsets, uint32_t B, uint32_t nchunks, xyzz_t* buckets,
                 uint32_t* slot_keys, xyzz_t* slot_pts, size_t slot_stride) {
@@ -290,16 +292,18 @@ k_accum_entries(const affine_t* __restrict__ table, const uint32_t* __restrict__
     if (start + 1 < end) {
         e_next = ent[start + 1];
         k_next = key[start + 1];
-        p_next = ldg_affine(table + (e_next & 0x7fffffffu));
+        if (PF) p_next = ldg_affine(table + (e_next & 0x7fffffffu));
     }
 #pragma unroll 1
     for (uint32_t pos = start + 1; pos < end; pos++) {
         const uint32_t ec = e_next, kc = k_next;
-        const affine_t p = p_next;
+        // PF: the table point of the next entry is fetched one iteration ahead (16 more live registers);
+        // otherwise only its index is, and the 64 B gather is issued at the top of its own iteration
+        const affine_t p = PF ? p_next : ldg_affine(table + (ec & 0x7fffffffu));
         if (pos + 1 < end) {
             e_next = ent[pos + 1];
             k_next = key[pos + 1];
-            p_next = ldg_affine(table + (e_next & 0x7fffffffu));
+            if (PF) p_next = ldg_affine(table + (e_next & 0x7fffffffu));
         }
         if (kc != cur) {
             emit_run(cur, acc, begins, true, first, bk, sk, sp, slot0);
@@ -528,8 +532,19 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     launch_digits<true>(c, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cur, ent, key, ent_cap); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_accum_entries", (double)G * n);
-    k_accum_entries<L1><<<dim3((nch1 + 127) / 128, (unsigned)G), 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa,
-                                                                              slotsA); }
+    {
+        static const char* ov = getenv("B2R_MSM_VARIANT");  // tuning hook (occupancy / prefetch variants)
+        const int variant = ov ? atoi(ov) : 0;
+        const dim3 ga((nch1 + 127) / 128, (unsigned)G);
+#define B2R_ACC(MINB, PF) k_accum_entries<L1, MINB, PF><<<ga, 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa, slotsA)
+        // measured on B200 (64 x 2^17 uniform scalars, tools/microbench.py): 4 CTAs/SM without the point prefetch 22.7 ms,
+        // with it 24.1 ms (spills); 5 or 6 CTAs/SM (96 / 80 registers, spills) 23.5 - 24.0 ms
+        switch (variant) {
+            case 1: B2R_ACC(4, true); break;
+            default: B2R_ACC(4, false); break;
+        }
+#undef B2R_ACC
+    } }
     B2R_LAUNCH_CHECK(ctx);
     // upper levels: ping-pong slot lists until one chunk remains
     const uint32_t* ik = ka;
