@@ -40,6 +40,11 @@ METRIC = "RSA-2048 pkcs1v15 proofs/sec at k=17"
 WORKLOAD = ("rsa2048_e65537_k17_batch64_per_gpu: full create_proof per instance (witness, 31 MSM 2^17, 22 iNTT 2^17, "
             "22 coset NTT 2^19 + 1 coset iNTT 2^19, lookups, permutation, quotient, 58 evals, GWC multiopen, Blake2b transcript)")
 MSM_BYTES_PER_TERM = 96  # 32 B scalar + 64 B affine base
+FULL_MSM_PER_PROOF, MSM_WINDOWS = 16, 16  # grand products 7, random poly 1, h pieces 4, GWC witnesses 4; ceil(255 / 16) windows
+# dram__bytes_read.sum + dram__bytes_write.sum of k_accum_entries from the ncu --set full capture in profiles/ (per scalar
+# of the launch); None until a capture of the current kernel exists
+ACCUM_TRAFFIC_BYTES_PER_TERM = None
+ACCUM_TRAFFIC_SOURCE = None
 
 
 def measured_peaks():
@@ -299,7 +304,19 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_launch": terms_per_launch * MSM_BYTES_PER_TERM,
                     "avg_launch_ms": kms / kcnt, "share_of_step": kms / ms,
-                    "note": "integer-ALU bound (254-bit field mul-adds), not HBM bound: see DESIGN.md roofline section"}
+                    "note": "integer-multiplier bound (254-bit field products), not HBM bound: see int_pipe and DESIGN.md section 4"}
+            # the roofline that binds this kernel (profiles/r01_pipebench.md): IMAD.WIDE issues at 32 lanes/clk/SM on B200, a
+            # Montgomery product is 128 of them, a mixed addition 10 products -> 148 SMs * 32 / 1280 additions per clock
+            sm_clk = 1.965e9
+            ceiling = 148 * 32 / 1280.0 * sm_clk / 1e9
+            full_adds = batch * FULL_MSM_PER_PROOF * n * MSM_WINDOWS * args.steps   # the 16 uniformly random scalar vectors per proof
+            roof["int_pipe"] = {"unit": "G mixed additions/s", "achieved": full_adds / (kms / 1e3) / 1e9, "peak": ceiling,
+                                "frac": full_adds / (kms / 1e3) / 1e9 / ceiling,
+                                "how": "2^17 scalars x 16 signed 16-bit windows x 16 full-size MSMs per proof (sparse columns not counted) / kernel time; "
+                                       "peak = 148 SMs x 32 IMAD.WIDE lanes/clk / (10 products x 128 IMAD.WIDE) at 1965 MHz"}
+            if ACCUM_TRAFFIC_BYTES_PER_TERM is not None:
+                roof["traffic"] = terms_per_launch * ACCUM_TRAFFIC_BYTES_PER_TERM
+                roof["traffic_source"] = ACCUM_TRAFFIC_SOURCE
         line = {
             "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -76,8 +76,22 @@ __device__ __forceinline__ void st_fe(fe_t* p, const fe_t& v) {
 template <int S>
 __global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
     constexpr uint32_t R = 1u << S;
+    // shared tile, split into the low and the high 16 bytes of every element: a warp's 128-bit accesses then touch
+    // consecutive banks (32-byte elements accessed whole are a 2-way bank conflict on every load and store)
     extern __shared__ uint4 smem_raw[];
-    fe_t* sm = reinterpret_cast<fe_t*>(smem_raw);
+    uint4* const sm_lo = smem_raw;
+    uint4* const sm_hi = smem_raw + ((size_t)(1u << S) << A.log_c);
+    auto lds = [&](uint32_t idx) {
+        const uint4 a = sm_lo[idx], b = sm_hi[idx];
+        fe_t r;
+        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+        return r;
+    };
+    auto sts = [&](uint32_t idx, const fe_t& v) {
+        sm_lo[idx] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        sm_hi[idx] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    };
     const uint32_t T = blockDim.x, tid = threadIdx.x;
     const uint32_t log_c = A.log_c, C = 1u << log_c, cmask = C - 1;
     const uint32_t log_cols = A.log_n - S;  // columns = n / R
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
         } else {
             v = Fr::zero();
         }
-        st_fe(sm + idx, v);
+        sts(idx, v);
     }
     __syncthreads();
 
@@ -120,21 +134,21 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
             const uint32_t ea = (base + (rp << log_cols)) << i;          // stage i, rows (r0, r0 + 2q)
             const uint32_t eb = (base + ((rp + q) << log_cols)) << i;    // stage i, rows (r0 + q, r0 + 3q)
             const uint32_t ec = ea << 1;                                 // stage i + 1, both pairs
-            const fe_t a0 = ld_fe(sm + i0), a1 = ld_fe(sm + i0 + st), a2 = ld_fe(sm + i0 + 2 * st), a3 = ld_fe(sm + i0 + 3 * st);
+            const fe_t a0 = lds(i0), a1 = lds(i0 + st), a2 = lds(i0 + 2 * st), a3 = lds(i0 + 3 * st);
             const fe_t u0 = Fr::add(a0, a2), u1 = Fr::add(a1, a3);
             fe_t d0 = Fr::sub(a0, a2), d1 = Fr::sub(a1, a3);
             if (ea) d0 = Fr::mul(d0, ld_fe_nc(A.tw + ea));
             d1 = Fr::mul(d1, ld_fe_nc(A.tw + eb));
             const fe_t wc = ld_fe_nc(A.tw + ec);
-            st_fe(sm + i0, Fr::add(u0, u1));
-            st_fe(sm + i0 + 2 * st, Fr::add(d0, d1));
+            sts(i0, Fr::add(u0, u1));
+            sts(i0 + 2 * st, Fr::add(d0, d1));
             fe_t v1 = Fr::sub(u0, u1), v3 = Fr::sub(d0, d1);
             if (ec) {
                 v1 = Fr::mul(v1, wc);
                 v3 = Fr::mul(v3, wc);
             }
-            st_fe(sm + i0 + st, v1);
-            st_fe(sm + i0 + 3 * st, v3);
+            sts(i0 + st, v1);
+            sts(i0 + 3 * st, v3);
         }
         __syncthreads();
     }
@@ -143,11 +157,11 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
             const uint32_t c = b & cmask, bf = b >> log_c;
             const uint32_t i0 = ((bf << 1) << log_c) + c, i1 = i0 + (1u << log_c);
             const uint32_t e = (((c0 + c) >> A.log_s) << A.log_s) << i;
-            const fe_t a = ld_fe(sm + i0), bb = ld_fe(sm + i1);
+            const fe_t a = lds(i0), bb = lds(i1);
             fe_t d = Fr::sub(a, bb);
             if (e) d = Fr::mul(d, ld_fe_nc(A.tw + e));
-            st_fe(sm + i0, Fr::add(a, bb));
-            st_fe(sm + i1, d);
+            sts(i0, Fr::add(a, bb));
+            sts(i1, d);
         }
         __syncthreads();
     }
@@ -158,7 +172,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
         for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
             uint32_t t = idx & (R - 1), c = idx >> S;
             uint32_t r = __brev(t) >> (32 - S);
-            fe_t v = ld_fe(sm + (r << log_c) + c);
+            fe_t v = lds((r << log_c) + c);
             uint32_t oi = ((c0 + c) << S) + t;
             if (A.post) v = Fr::mul(v, A.post3[oi % 3u]);
             st_fe(y + oi, v);
@@ -169,7 +183,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
             uint32_t t = __brev(r) >> (32 - S);
             uint32_t col = c0 + c, q = col & smask, pp = col >> A.log_s;
             uint32_t oi = q + (pp << (A.log_s + S)) + (t << A.log_s);
-            fe_t v = ld_fe(sm + idx);
+            fe_t v = lds(idx);
             if (A.post) v = Fr::mul(v, A.post3[oi % 3u]);
             st_fe(y + oi, v);
         }
