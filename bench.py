@@ -41,10 +41,13 @@ WORKLOAD = ("rsa2048_e65537_k17_batch64_per_gpu: full create_proof per instance 
             "22 coset NTT 2^19 + 1 coset iNTT 2^19, lookups, permutation, quotient, 58 evals, GWC multiopen, Blake2b transcript)")
 MSM_BYTES_PER_TERM = 96  # 32 B scalar + 64 B affine base
 FULL_MSM_PER_PROOF, MSM_WINDOWS = 16, 16  # grand products 7, random poly 1, h pieces 4, GWC witnesses 4; ceil(255 / 16) windows
-# dram__bytes_read.sum + dram__bytes_write.sum of k_accum_entries from the ncu --set full capture in profiles/ (per scalar
-# of the launch); None until a capture of the current kernel exists
-ACCUM_TRAFFIC_BYTES_PER_TERM = None
-ACCUM_TRAFFIC_SOURCE = None
+# dram__bytes_read.sum + dram__bytes_write.sum of k_accum_entries from the ncu --set full capture summarised in
+# profiles/r01_ncu_final.md: the launch over 409 grand-product columns (full-size scalars) moved 43.61 GB + 3.49 GB
+ACCUM_TRAFFIC_BYTES = 47.1e9
+ACCUM_TRAFFIC_VECTORS = 409
+ACCUM_TRAFFIC_SOURCE = ("ncu --set full, one k_accum_entries launch over 409 x 2^17 full-size scalars: 43.61 GB read + 3.49 GB written "
+                        "(algorithmic 5.15 GB; the rest is the 16 x 64 B table gathers per scalar of the resident-table design, "
+                        "47.6 % L2 hits) - profiles/r01_ncu_final.md")
 
 
 def measured_peaks():
@@ -314,9 +317,9 @@ def main():
                                 "frac": full_adds / (kms / 1e3) / 1e9 / ceiling,
                                 "how": "2^17 scalars x 16 signed 16-bit windows x 16 full-size MSMs per proof (sparse columns not counted) / kernel time; "
                                        "peak = 148 SMs x 32 IMAD.WIDE lanes/clk / (10 products x 128 IMAD.WIDE) at 1965 MHz"}
-            if ACCUM_TRAFFIC_BYTES_PER_TERM is not None:
-                roof["traffic"] = terms_per_launch * ACCUM_TRAFFIC_BYTES_PER_TERM
-                roof["traffic_source"] = ACCUM_TRAFFIC_SOURCE
+            roof["traffic"] = ACCUM_TRAFFIC_BYTES
+            roof["traffic_algorithmic_bytes_of_that_launch"] = ACCUM_TRAFFIC_VECTORS * n * MSM_BYTES_PER_TERM
+            roof["traffic_source"] = ACCUM_TRAFFIC_SOURCE
         line = {
             "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
