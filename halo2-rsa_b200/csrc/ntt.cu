@@ -278,11 +278,14 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         int base = log_n / npass, extra = log_n % npass;
         for (int p = 0; p < npass; p++) S[p] = base + (p < extra ? 1 : 0);
     }
-    // ping-pong: pass p reads buf[p&1], writes the other; arrange that the last pass lands in `out`
-    fe_t* tmp = nullptr;
-    if (npass > 1 || in == out) {
-        B2R_TRY(scratch_get(ctx, SC_NTT_PING, batch * n * sizeof(fe_t), (void**)&tmp));
-    }
+    // Stockham passes are out of place.  Destinations alternate so that the LAST pass writes `out` and no pass writes
+    // the buffer it reads: out of place (in != out) alternates out / ping backwards from the end; in place uses
+    // ping (and pong when the pass count is odd).  No copy-back pass (the first version always started in the scratch
+    // buffer and copied 16 MiB per 2^19 transform back: 22 GB per 64-proof step).
+    fe_t *ping = nullptr, *pong = nullptr;
+    const bool in_place = (const void*)in == (const void*)out;
+    if (npass > 1 || in_place) B2R_TRY(scratch_get(ctx, SC_NTT_PING, batch * n * sizeof(fe_t), (void**)&ping));
+    if (in_place && npass > 1 && (npass & 1)) B2R_TRY(scratch_get(ctx, SC_NTT_PONG, batch * n * sizeof(fe_t), (void**)&pong));
     fe_t n_inv = Fr::zero();
     fe_t zeta = fr_zeta(), zeta2 = Fr::sqr(zeta);
     if (mode == MODE_INV || mode == MODE_COSET_INV) n_inv = Fr::inv(fr_from_u64(n));
@@ -293,28 +296,17 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
     uint32_t log_s = 0;
     for (int p = 0; p < npass; p++) {
         bool last = (p == npass - 1);
-        // destination: last pass -> out; otherwise alternate so that we never write what we read
         fe_t* dst;
-        uint64_t dst_stride;
-        if (last) {
-            dst = out;
-            dst_stride = out_stride;
-            if (src == out) {  // single pass in place: go through tmp then copy back
-                dst = tmp;
-                dst_stride = n;
-            }
+        if (!in_place) {
+            dst = ((npass - 1 - p) & 1) ? ping : out;
+        } else if (npass == 1) {
+            dst = ping;  // single pass in place: through the scratch buffer, copied back below
+        } else if (npass & 1) {
+            dst = last ? out : (p & 1 ? pong : ping);  // in -> ping -> pong -> ... -> out
         } else {
-            // intermediate: use tmp unless src is tmp, then use out (out is free: in was consumed)
-            if (src != tmp) {
-                dst = tmp;
-                dst_stride = n;
-            } else {
-                dst = out;
-                dst_stride = out_stride;
-            }
+            dst = (p & 1) ? out : ping;                // in -> ping -> out -> ping -> out
         }
-        // if the remaining number of passes would make the last one read from `out`, that is
-        // handled by the in-place branch above (one extra D2D copy).
+        const uint64_t dst_stride = (dst == out) ? out_stride : n;
         NttPassArgs A;
         A.x = src;
         A.y = dst;
