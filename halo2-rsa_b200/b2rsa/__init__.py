@@ -66,6 +66,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_rsa_commit_batch": [vp, vp, vp, vp, vp, vp, sz, u64, u32, u32, vp, vp, vp, vp],
         "b2r_rsa_commit_batch_dev": [vp, vp, vp, vp, vp, vp, sz, u64, u32, u32, vp, vp, vp, vp],
         "b2r_rsa_program_build": [vp, u32, vp, sz, u32, C.POINTER(vp)],
+        "b2r_rsa_program_build_var": [vp, u32, u32, u32, C.POINTER(vp)],
+        "b2r_bigint_program_build": [vp, u32, u32, u32, u32, C.POINTER(vp)],
+        "b2r_prog_aux_words": [vp],
         "b2r_prog_free": [vp, vp],
         "b2r_prog_info": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
         "b2r_rsa_witness_batch": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
@@ -277,6 +280,20 @@ class Context:
         self._ck(self.lib.b2r_rsa_program_build(self.h, bits_len, _host_ptr(e_le), e_le.size, k, C.byref(h)))
         return RsaProgram(self, h, bits_len, k)
 
+    def rsa_program_var(self, bits_len: int, k: int, exp_limb_bits: int) -> "RsaProgram":
+        """pkcs1v15 circuit with RSAPubE::Var: third input array = hash limbs then the exponent word"""
+        h = C.c_void_p()
+        self._ck(self.lib.b2r_rsa_program_build_var(self.h, bits_len, exp_limb_bits, k, C.byref(h)))
+        return RsaProgram(self, h, bits_len, k)
+
+    BIGINT_OPS = {"refresh": 6, "add_mod": 7, "sub_mod": 8, "pow_mod": 9}
+
+    def bigint_program(self, op: str, bits_len: int, k: int, exp_limb_bits: int = 5) -> "RsaProgram":
+        """one BigIntInstructions method as the reference's unit-test circuits drive it; witness inputs (a, b, n | e)"""
+        h = C.c_void_p()
+        self._ck(self.lib.b2r_bigint_program_build(self.h, self.BIGINT_OPS[op], bits_len, exp_limb_bits, k, C.byref(h)))
+        return RsaProgram(self, h, bits_len, k)
+
 
 class Bases:
     def __init__(self, ctx: Context, h, n: int):
@@ -341,6 +358,7 @@ class RsaProgram:
     def __init__(self, ctx: Context, h, bits_len: int, k: int):
         self.ctx, self.h, self.bits_len, self.k = ctx, h, bits_len, k
         self.num_limbs = bits_len // 64
+        self.aux_words = int(ctx.lib.b2r_prog_aux_words(h))   # words per instance of the third input array
 
     def info(self):
         r, v, l = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -354,7 +372,7 @@ class RsaProgram:
         hash_limbs = np.ascontiguousarray(hash_limbs, dtype=np.uint64)
         batch = n_limbs.shape[0]
         assert n_limbs.shape == (batch, self.num_limbs) and sig_limbs.shape == (batch, self.num_limbs)
-        assert hash_limbs.shape == (batch, 4)
+        assert hash_limbs.shape == (batch, self.aux_words)
         advice = np.empty((batch, 5, 1 << self.k, 4), dtype=np.uint64)
         valid = np.zeros(batch, dtype=np.uint8)
         self.ctx._ck(self.ctx.lib.b2r_rsa_witness_batch(

@@ -82,6 +82,23 @@ struct U256 {
             if (l[i]) return 64 * i + (64 - __builtin_clzll(l[i]));
         return 0;
     }
+    U256 shr(unsigned b) const {
+        U256 r;
+        const unsigned w = b >> 6, s = b & 63;
+        for (unsigned i = 0; i + w < 4; i++) {
+            r.l[i] = l[i + w] >> s;
+            if (s && i + w + 1 < 4) r.l[i] |= l[i + w + 1] << (64 - s);
+        }
+        return r;
+    }
+    U256 low(unsigned b) const {  // value mod 2^b
+        U256 r = *this;
+        for (unsigned i = 0; i < 4; i++) {
+            if (64 * i >= b) r.l[i] = 0;
+            else if (64 * (i + 1) > b) r.l[i] &= (~0ull) >> (64 * (i + 1) - b);
+        }
+        return r;
+    }
     int pow2_log() const {  // b if value == 2^b, else -1
         unsigned b = bits();
         if (b == 0) return -1;
@@ -349,6 +366,36 @@ class MainGate {
         ctx.constrain_equal(o[0], o[2]);
         return o[4];
     }
+    // MainGate::compose (maingate, third party): sum of the terms, laid out like decompose(): 4 terms per row in a..d,
+    // the running remainder (base -1) in e, rows chained with CombineToNextAdd(1); returns the first row's e cell.
+    // `total` is the value node of the whole sum; the remainders of later rows are `total` with its low bits cleared,
+    // which holds because every caller composes ascending powers of two (to_bits).
+    AssignedValue compose_bits(RegionCtx& ctx, const std::vector<AssignedCondition>& bits, int32_t total) const {
+        const size_t n = bits.size(), nchunks = (n - 1) / 4 + 1;
+        AssignedValue result;
+        for (size_t ch = 0; ch < nchunks; ch++) {
+            std::vector<Term> t;
+            for (size_t j = 4 * ch; j < 4 * ch + 4 && j < n; j++) t.push_back(Term::assigned(bits[j], U256::pow2((unsigned)j)));
+            while (t.size() < 4) t.push_back(Term::zero());
+            const int32_t rem = ch == 0 ? total : ctx.op1(OP_CLEARLOW, total, (uint32_t)(4 * ch));
+            t.push_back(Term::unassigned_to_sub(rem));
+            const bool is_final = ch == nchunks - 1;
+            auto o = apply(ctx, t, U256(0), is_final ? CombinationOption::OneLinerAdd() : CombinationOption::CombineToNextAdd(U256(1)));
+            if (ch == 0) result = o[4];
+        }
+        return result;
+    }
+    // MainGate::to_bits (maingate, third party): number_of_bits boolean cells, least significant first, whose
+    // composition is constrained equal to `composed`
+    std::vector<AssignedCondition> to_bits(RegionCtx& ctx, const AssignedValue& composed, unsigned number_of_bits) const {
+        if (number_of_bits == 0 || number_of_bits > 254) throw SynthError(-1, "to_bits: number_of_bits out of range");
+        std::vector<AssignedCondition> bits;
+        for (unsigned i = 0; i < number_of_bits; i++) bits.push_back(assign_bit(ctx, ctx.op1(OP_SUBLIMB, composed.vid, i, 1)));
+        const int32_t total = ctx.op1(OP_LOWBITS, composed.vid, number_of_bits);  // what the bits compose to
+        AssignedValue result = compose_bits(ctx, bits, total);
+        assert_equal(ctx, result, composed);
+        return bits;
+    }
     // invert(): r bit, then (a * a') - 1 + r = 0 and r * a' - r = 0
     AssignedCondition is_zero(RegionCtx& ctx, const AssignedValue& a) const {
         int32_t rv = ctx.op1(OP_ISZERO, a.vid);
@@ -571,6 +618,124 @@ class BigIntChip {
         return c;
     }
     AssignedInteger square(RegionCtx& ctx, const AssignedInteger& a) const { return mul(ctx, a, a); }
+    // RefreshAux::new (src/big_integer/mod.rs:431-482): how many extra limbs every limb of a product of num_limbs_l x
+    // num_limbs_r maximal limbs spills into when it is cut back to limb_width bits
+    static std::vector<size_t> refresh_increased_limbs(unsigned limb_width, size_t num_limbs_l, size_t num_limbs_r) {
+        const U256 max_limb = U256::pow2(limb_width).sub(U256(1));
+        const size_t d = num_limbs_l + num_limbs_r - 1;
+        std::vector<U256> muled;
+        for (size_t i = 0; i < d; i++) {
+            size_t j = num_limbs_r >= i + 1 ? 0 : i + 1 - num_limbs_r;
+            U256 acc;
+            while (j < num_limbs_l && j <= i) {
+                acc = acc.add(max_limb.mul(max_limb));
+                j++;
+            }
+            muled.push_back(acc);
+        }
+        std::vector<size_t> inc;
+        size_t cur_d = 0;
+        const size_t max_d = d;
+        while (cur_d <= max_d) {
+            if (muled.size() <= cur_d) muled.push_back(U256());
+            const unsigned bits = muled[cur_d].bits();
+            const size_t num_chunks = bits % limb_width == 0 ? bits / limb_width : bits / limb_width + 1;
+            if (num_chunks == 0) throw SynthError(-1, "RefreshAux: empty limb");  // the reference underflows here (usize)
+            inc.push_back(num_chunks - 1);
+            std::vector<U256> chunks;
+            for (size_t c = 0; c < num_chunks; c++) {
+                chunks.push_back(muled[cur_d].low(limb_width));
+                muled[cur_d] = muled[cur_d].shr(limb_width);
+            }
+            for (size_t j = 0; j < num_chunks; j++) {
+                if (muled.size() <= cur_d + j) muled.push_back(U256());
+                muled[cur_d + j] = muled[cur_d + j].add(chunks[j]);
+            }
+            cur_d++;
+        }
+        return inc;
+    }
+    // chip.rs:168-233: Muled -> Fresh
+    AssignedInteger refresh(RegionCtx& ctx, const AssignedInteger& a, size_t num_limbs_l, size_t num_limbs_r) const {
+        const std::vector<size_t> inc = refresh_increased_limbs(limb_width, num_limbs_l, num_limbs_r);
+        if (a.num_limbs() != num_limbs_l + num_limbs_r - 1) throw SynthError(-6, "refresh: limb count does not match the aux data");
+        const size_t num_limbs_fresh = inc.size();
+        AssignedValue zero_val = main_gate_.assign_constant(ctx, U256(0));
+        std::vector<AssignedValue> refreshed = a.limbs;
+        while (refreshed.size() < num_limbs_fresh) refreshed.push_back(zero_val);
+        AssignedValue limb_max = main_gate_.assign_constant(ctx, U256::pow2(limb_width));
+        for (size_t i = 0; i < num_limbs_fresh; i++) {
+            AssignedValue limb = refreshed[i];
+            for (size_t j = 0; j < inc[i] + 1; j++) {
+                AssignedValue q, n;
+                div_mod_main_gate(ctx, limb, limb_max, &q, &n);
+                if (j == 0) {
+                    refreshed[i] = n;
+                } else {
+                    if (i + j >= refreshed.size()) throw SynthError(-6, "refresh: carry past the last limb");  // index panic in the reference
+                    refreshed[i + j] = main_gate_.add(ctx, refreshed[i + j], n);
+                }
+                limb = q;
+            }
+            main_gate_.assert_zero(ctx, limb);
+        }
+        AssignedInteger r;
+        for (size_t i = 0; i < num_limbs_fresh; i++) {
+            AssignedValue range_assigned = range_chip_.assign(ctx, refreshed[i].vid, sublimb_bit_len(limb_width), limb_width);
+            main_gate_.assert_equal(ctx, refreshed[i], range_assigned);
+            r.limbs.push_back(refreshed[i]);
+        }
+        return r;
+    }
+    // chip.rs:452-481
+    AssignedInteger add_mod(RegionCtx& ctx, const AssignedInteger& a, const AssignedInteger& b, const AssignedInteger& n) const {
+        AssignedInteger added = add(ctx, a, b);
+        AssignedValue is_overflowed;
+        AssignedInteger subed = sub(ctx, added, n, &is_overflowed);
+        const size_t nl = subed.num_limbs();
+        if (nl < added.num_limbs()) throw SynthError(-6, "add_mod: limb count underflow");
+        AssignedValue zero_value = main_gate_.assign_constant(ctx, U256(0));
+        added.extend_limbs(nl - added.num_limbs(), zero_value);
+        std::vector<AssignedValue> res;
+        for (size_t i = 0; i < nl; i++) res.push_back(main_gate_.select(ctx, added.limb(i), subed.limb(i), is_overflowed));
+        for (size_t i = n.num_limbs(); i < nl; i++) main_gate_.assert_zero(ctx, res[i]);
+        AssignedInteger r;
+        r.limbs.assign(res.begin(), res.begin() + n.num_limbs());
+        return r;
+    }
+    // chip.rs:495-529
+    AssignedInteger sub_mod(RegionCtx& ctx, const AssignedInteger& a, const AssignedInteger& b, const AssignedInteger& n) const {
+        AssignedValue is_overflowed1, is_overflowed2;
+        AssignedInteger subed1 = sub(ctx, a, b, &is_overflowed1);
+        AssignedInteger subed2 = sub(ctx, n, subed1, &is_overflowed2);
+        main_gate_.assert_zero(ctx, is_overflowed2);
+        const size_t nl = subed2.num_limbs();
+        if (nl < subed1.num_limbs()) throw SynthError(-6, "sub_mod: limb count underflow");
+        AssignedValue zero_value = main_gate_.assign_constant(ctx, U256(0));
+        subed1.extend_limbs(nl - subed1.num_limbs(), zero_value);
+        std::vector<AssignedValue> res;
+        for (size_t i = 0; i < nl; i++) res.push_back(main_gate_.select(ctx, subed2.limb(i), subed1.limb(i), is_overflowed1));
+        for (size_t i = n.num_limbs(); i < nl; i++) main_gate_.assert_zero(ctx, res[i]);
+        AssignedInteger r;
+        r.limbs.assign(res.begin(), res.begin() + n.num_limbs());
+        return r;
+    }
+    // chip.rs:664-696: variable exponent, exp_limb_bits bits taken from every limb of e (least significant first)
+    AssignedInteger pow_mod(RegionCtx& ctx, const AssignedInteger& a, const AssignedInteger& e, const AssignedInteger& n, unsigned exp_limb_bits) const {
+        std::vector<AssignedValue> e_bits;
+        for (const auto& limb : e.limbs) {
+            std::vector<AssignedCondition> bits = main_gate_.to_bits(ctx, limb, exp_limb_bits);
+            e_bits.insert(e_bits.end(), bits.begin(), bits.end());
+        }
+        AssignedInteger acc = assign_constant_fresh(ctx, {1});
+        AssignedInteger squared = a;
+        for (const auto& e_bit : e_bits) {
+            AssignedInteger muled = mul_mod(ctx, acc, squared, n);
+            for (size_t j = 0; j < acc.num_limbs(); j++) acc.limbs[j] = main_gate_.select(ctx, muled.limb(j), acc.limb(j), e_bit);
+            squared = square_mod(ctx, squared, n);
+        }
+        return acc;
+    }
     // chip.rs:542-629
     AssignedInteger mul_mod(RegionCtx& ctx, const AssignedInteger& a, const AssignedInteger& b, const AssignedInteger& n) const {
         size_t n1 = a.num_limbs(), n2 = b.num_limbs();
@@ -759,6 +924,7 @@ class BigIntChip {
 struct AssignedRSAPublicKey {
     AssignedInteger n;
     std::vector<uint8_t> e_fix;  // RSAPubE::Fix, little-endian bytes
+    AssignedInteger e_var;       // RSAPubE::Var (src/lib.rs:58-63): assigned exponent limbs; empty for Fix
 };
 struct AssignedRSASignature {
     AssignedInteger c;
@@ -782,6 +948,14 @@ class RSAChip {
         pk.e_fix = e_fix;
         return pk;
     }
+    // chip.rs:58-70, RSAPubE::Var: the exponent is a witness too
+    AssignedRSAPublicKey assign_public_key_var(RegionCtx& ctx, const UnassignedInteger& n, const UnassignedInteger& e) const {
+        AssignedRSAPublicKey pk;
+        BigIntChip chip = bigint_chip();
+        pk.n = chip.assign_integer(ctx, n);
+        pk.e_var = chip.assign_integer(ctx, e);
+        return pk;
+    }
     // chip.rs:80-88
     AssignedRSASignature assign_signature(RegionCtx& ctx, const UnassignedInteger& c) const {
         AssignedRSASignature s;
@@ -792,6 +966,7 @@ class RSAChip {
     AssignedInteger modpow_public_key(RegionCtx& ctx, const AssignedInteger& x, const AssignedRSAPublicKey& pk) const {
         BigIntChip chip = bigint_chip();
         chip.assert_in_field(ctx, x, pk.n);
+        if (pk.e_var.num_limbs()) return chip.pow_mod(ctx, x, pk.e_var, pk.n, exp_limb_bits);
         return chip.pow_mod_fixed_exp(ctx, x, pk.e_fix, pk.n);
     }
     // chip.rs:128-199
@@ -873,6 +1048,62 @@ inline AssignedValue record_rsa_pkcs1v15(RegionCtx& rc, unsigned bits_len, const
     // region 3 (bench.rs:213-221)
     main_gate.assert_one(rc, is_valid);
     return is_valid;
+}
+
+// pkcs1v15 circuit with RSAPubE::Var (src/chip.rs:372-390 test_rsa_signature_with_hash_circuit's shape): the exponent is an
+// assigned one-limb integer of which `exp_limb_bits` bits are used.  Inputs: n limbs, signature limbs, hash limbs, then e.
+inline AssignedValue record_rsa_pkcs1v15_var(RegionCtx& rc, unsigned bits_len, unsigned exp_limb_bits) {
+    const unsigned nl = bits_len / 64;
+    configure_range_tags(rc, nl);
+    RSAChip rsa_chip(bits_len, exp_limb_bits);
+    BigIntChip bigint_chip = rsa_chip.bigint_chip();
+    MainGate main_gate;
+    UnassignedInteger sig_u, n_u, hash_u, e_u;
+    for (unsigned i = 0; i < nl; i++) n_u.limbs.push_back(rc.input(i));
+    for (unsigned i = 0; i < nl; i++) sig_u.limbs.push_back(rc.input(nl + i));
+    for (unsigned i = 0; i < 4; i++) hash_u.limbs.push_back(rc.input(2 * nl + i));
+    e_u.limbs.push_back(rc.input(2 * nl + 4));
+    AssignedRSASignature sign = rsa_chip.assign_signature(rc, sig_u);
+    AssignedRSAPublicKey public_key = rsa_chip.assign_public_key_var(rc, n_u, e_u);
+    AssignedInteger hashed = bigint_chip.assign_integer(rc, hash_u);
+    AssignedValue is_valid = rsa_chip.verify_pkcs1v15_signature(rc, public_key, hashed, sign);
+    main_gate.assert_one(rc, is_valid);
+    return is_valid;
+}
+
+// Single BigIntChip operations, as the reference's in-file test circuits drive them (src/big_integer/chip.rs:1470-2313).
+// Inputs (value nodes): a = 0..nl-1, b = nl..2nl-1, n = 2nl..3nl-1, e = 3nl.  Returns the cell whose value reports the
+// outcome (the last limb of the result); `out` receives the result limbs.
+enum BigIntTestOp : uint32_t { BT_REFRESH = 6, BT_ADD_MOD = 7, BT_SUB_MOD = 8, BT_POW_MOD = 9 };
+inline AssignedValue record_bigint_op(RegionCtx& rc, uint32_t op, unsigned bits_len, unsigned exp_limb_bits, AssignedInteger* out) {
+    const unsigned nl = bits_len / 64;
+    configure_range_tags(rc, nl);
+    BigIntChip chip(64, bits_len);
+    UnassignedInteger a_u, b_u, n_u, e_u;
+    for (unsigned i = 0; i < nl; i++) a_u.limbs.push_back(rc.input(i));
+    for (unsigned i = 0; i < nl; i++) b_u.limbs.push_back(rc.input(nl + i));
+    for (unsigned i = 0; i < nl; i++) n_u.limbs.push_back(rc.input(2 * nl + i));
+    e_u.limbs.push_back(rc.input(3 * nl));
+    AssignedInteger a = chip.assign_integer(rc, a_u), r;
+    if (op == BT_REFRESH) {            // chip.rs:1861-1899
+        AssignedInteger b = chip.assign_integer(rc, b_u);
+        AssignedInteger ab = chip.mul(rc, a, b), ba = chip.mul(rc, b, a);
+        r = chip.refresh(rc, ab, nl, nl);
+        AssignedInteger ba_r = chip.refresh(rc, ba, nl, nl);
+        chip.assert_equal_fresh(rc, r, ba_r);
+    } else if (op == BT_ADD_MOD || op == BT_SUB_MOD) {   // chip.rs:1948-2110
+        AssignedInteger b = chip.assign_integer(rc, b_u);
+        AssignedInteger n = chip.assign_integer(rc, n_u);
+        r = op == BT_ADD_MOD ? chip.add_mod(rc, a, b, n) : chip.sub_mod(rc, a, b, n);
+    } else if (op == BT_POW_MOD) {     // chip.rs:2229-2271 (the exponent assigned as a witness, as RSAPubE::Var does)
+        AssignedInteger e = chip.assign_integer(rc, e_u);
+        AssignedInteger n = chip.assign_integer(rc, n_u);
+        r = chip.pow_mod(rc, a, e, n, exp_limb_bits);
+    } else {
+        throw SynthError(-1, "record_bigint_op: unknown operation");
+    }
+    if (out) *out = r;
+    return r.limbs.back();
 }
 
 }  // namespace circuit

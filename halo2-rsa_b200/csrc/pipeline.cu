@@ -119,7 +119,8 @@ int32_t b2r_rsa_commit_batch(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases
         return fail(ctx, B2R_ERR_INVALID, "rsa_commit: null pointer");
     if (batch == 0) return 0;
     const size_t limbs = (size_t)b2r_prog_num_limbs(prog);
-    const size_t in_words = batch * (2 * limbs + 4);
+    const size_t aux = (size_t)b2r_prog_aux_words(prog);
+    const size_t in_words = batch * (2 * limbs + aux);
     char* d = nullptr;
     size_t in_al = (in_words * 8 + 255) & ~(size_t)255;
     size_t cm_al = (batch * 5 * sizeof(b2r_g1_affine) + 255) & ~(size_t)255;
@@ -131,7 +132,7 @@ int32_t b2r_rsa_commit_batch(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases
     uint8_t* d_valid = (uint8_t*)(d + in_al + cm_al);
     B2R_CUDA(ctx, cudaMemcpyAsync(d_n, n_limbs, batch * limbs * 8, cudaMemcpyHostToDevice, ctx->stream));
     B2R_CUDA(ctx, cudaMemcpyAsync(d_s, sig_limbs, batch * limbs * 8, cudaMemcpyHostToDevice, ctx->stream));
-    B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * 4 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * aux * 8, cudaMemcpyHostToDevice, ctx->stream));
     B2R_TRY(b2r_rsa_commit_batch_dev(ctx, prog, g_lagrange, d_n, d_s, d_h, batch, blind_seed, k, ext_k, advice_dev, ext_dev, d_cm, d_valid));
     B2R_CUDA(ctx, cudaMemcpyAsync(commitments, d_cm, batch * 5 * sizeof(b2r_g1_affine), cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaMemcpyAsync(is_valid, d_valid, batch, cudaMemcpyDeviceToHost, ctx->stream));

@@ -20,6 +20,7 @@ struct b2r_prog {
     uint32_t rows_used = 0, num_values = 0, num_levels = 0;
     int32_t is_valid_vid = -1;
     uint32_t num_inputs = 0;
+    uint32_t aux_words = 4;  // 64-bit words per instance in the third input array: 4 hash limbs (+ the exponent for RSAPubE::Var)
     // device
     Node* d_nodes = nullptr;
     LevelRange* d_levels = nullptr;

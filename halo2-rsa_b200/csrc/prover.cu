@@ -1109,7 +1109,7 @@ static int32_t prove_all(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, co
     size_t G = std::max<size_t>(1, std::min<size_t>(64, ((size_t)48 << 30) / per_proof));
     for (size_t p0 = 0; p0 < batch; p0 += G) {
         const uint32_t g = (uint32_t)std::min(G, batch - p0);
-        B2R_TRY(prove_group(ctx, pk, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * 4, g, seed, (uint32_t)p0, proofs + p0 * proof_bytes, status + p0,
+        B2R_TRY(prove_group(ctx, pk, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * pk->prog->aux_words, g, seed, (uint32_t)p0, proofs + p0 * proof_bytes, status + p0,
                             (size_t)proof_bytes));
     }
     return 0;
@@ -1132,11 +1132,12 @@ int32_t b2r_rsa_prove_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_li
     if (batch == 0) return 0;
     const size_t nl = pk->prog->num_limbs;
     uint64_t* d_in = nullptr;
-    B2R_TRY(scratch_get(ctx, SC_MISC, batch * (2 * nl + 4) * 8 + 256, (void**)&d_in));
+    const size_t aw = pk->prog->aux_words;
+    B2R_TRY(scratch_get(ctx, SC_MISC, batch * (2 * nl + aw) * 8 + 256, (void**)&d_in));
     uint64_t *d_n = d_in, *d_s = d_in + batch * nl, *d_h = d_in + 2 * batch * nl;
     B2R_CUDA(ctx, cudaMemcpyAsync(d_n, n_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
     B2R_CUDA(ctx, cudaMemcpyAsync(d_s, sig_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
-    B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * 4 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * aw * 8, cudaMemcpyHostToDevice, ctx->stream));
     return prove_all(ctx, pk, d_n, d_s, d_h, batch, seed, proofs, status);
 }
 

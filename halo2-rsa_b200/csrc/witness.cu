@@ -241,7 +241,7 @@ struct WitnessArgs {
     const uint64_t* hash_limbs;
     fe_t* values;  // [batch][num_values]
     uint8_t* is_valid;
-    uint32_t num_levels, num_values, num_limbs, big_words;
+    uint32_t num_levels, num_values, num_limbs, big_words, aux_words;
     int32_t is_valid_vid;
 };
 
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(1024) k_witness_eval(const WitnessArgs A) {
                     uint32_t w = nd.a, nl = A.num_limbs;
                     uint64_t v = w < nl ? A.n_limbs[(size_t)p * nl + w]
                                : w < 2 * nl ? A.sig_limbs[(size_t)p * nl + (w - nl)]
-                                            : A.hash_limbs[(size_t)p * 4 + (w - 2 * nl)];
+                                            : A.hash_limbs[(size_t)p * A.aux_words + (w - 2 * nl)];
                     r = fe_from_u64_dev(v);
                     break;
                 }
@@ -431,25 +431,24 @@ static void prog_release(b2r_prog* p) {
 
 extern "C" {
 
-int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_le, size_t e_len, uint32_t k, b2r_prog** out) {
-    if (!ctx) return B2R_ERR_INVALID;
-    if (!out || !e_le || e_len == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: null argument");
+}  // extern "C"
+
+// shared tail of the program builders: `record` fills the RegionCtx and returns the cell that reports the outcome
+template <class Rec>
+static int32_t build_program(b2r_ctx* ctx, uint32_t bits_len, uint32_t k, uint32_t aux_words, Rec record, b2r_prog** out) {
     *out = nullptr;
-    if (bits_len < 512 || bits_len > 4096 || bits_len % 64) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: bits_len must be a multiple of 64 in [512, 4096]");
-    if (k < 4 || k > 24) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: k out of range");
-    bool e_nonzero = false;
-    for (size_t i = 0; i < e_len; i++) e_nonzero |= e_le[i] != 0;
-    if (!e_nonzero) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: exponent is zero");
+    if (bits_len < 512 || bits_len > 4096 || bits_len % 64) return fail(ctx, B2R_ERR_INVALID, "program_build: bits_len must be a multiple of 64 in [512, 4096]");
+    if (k < 4 || k > 24) return fail(ctx, B2R_ERR_INVALID, "program_build: k out of range");
     b2r_prog* prog = new b2r_prog();
     prog->bits_len = bits_len;
     prog->num_limbs = bits_len / 64;
     prog->k = k;
-    prog->num_inputs = 2 * prog->num_limbs + 4;
+    prog->aux_words = aux_words;
+    prog->num_inputs = 2 * prog->num_limbs + aux_words;
     try {
         RegionCtx rc((1u << k) - BLINDING_ROWS);
-        std::vector<uint8_t> e(e_le, e_le + e_len);
-        AssignedValue is_valid = record_rsa_pkcs1v15(rc, bits_len, e);
-        int32_t r = finalize_program(ctx, rc, is_valid, prog);
+        AssignedValue result = record(rc);
+        int32_t r = finalize_program(ctx, rc, result, prog);
         if (r) {
             prog_release(prog);
             return r;
@@ -465,6 +464,37 @@ int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_
     return 0;
 }
 
+extern "C" {
+
+int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_le, size_t e_len, uint32_t k, b2r_prog** out) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!out || !e_le || e_len == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: null argument");
+    *out = nullptr;
+    if (bits_len < 512 || bits_len > 4096 || bits_len % 64) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: bits_len must be a multiple of 64 in [512, 4096]");
+    if (k < 4 || k > 24) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: k out of range");
+    bool e_nonzero = false;
+    for (size_t i = 0; i < e_len; i++) e_nonzero |= e_le[i] != 0;
+    if (!e_nonzero) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: exponent is zero");
+    std::vector<uint8_t> e(e_le, e_le + e_len);
+    return build_program(ctx, bits_len, k, 4, [&](RegionCtx& rc) { return record_rsa_pkcs1v15(rc, bits_len, e); }, out);
+}
+
+int32_t b2r_rsa_program_build_var(b2r_ctx* ctx, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!out) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build_var: null argument");
+    if (exp_limb_bits == 0 || exp_limb_bits > 64) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build_var: exp_limb_bits must be in [1, 64]");
+    return build_program(ctx, bits_len, k, 5, [&](RegionCtx& rc) { return record_rsa_pkcs1v15_var(rc, bits_len, exp_limb_bits); }, out);
+}
+
+int32_t b2r_bigint_program_build(b2r_ctx* ctx, uint32_t op, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!out) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: null argument");
+    if (op < BT_REFRESH || op > BT_POW_MOD) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: unknown operation");
+    if (exp_limb_bits == 0 || exp_limb_bits > 64) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: exp_limb_bits must be in [1, 64]");
+    // inputs a | b | n | e: the third array carries n and e (num_limbs + 1 words per instance)
+    return build_program(ctx, bits_len, k, bits_len / 64 + 1, [&](RegionCtx& rc) { return record_bigint_op(rc, op, bits_len, exp_limb_bits, nullptr); }, out);
+}
+
 int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog* prog) {
     if (!ctx || !prog) return B2R_ERR_INVALID;
     cudaStreamSynchronize(ctx->stream);
@@ -473,6 +503,7 @@ int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog* prog) {
 }
 
 int32_t b2r_prog_num_limbs(const b2r_prog* prog) { return prog ? (int32_t)prog->num_limbs : B2R_ERR_INVALID; }
+int32_t b2r_prog_aux_words(const b2r_prog* prog) { return prog ? (int32_t)prog->aux_words : B2R_ERR_INVALID; }
 
 int32_t b2r_prog_info(const b2r_prog* prog, uint64_t* rows_used, uint64_t* num_values, uint64_t* num_levels) {
     if (!prog) return B2R_ERR_INVALID;
@@ -512,7 +543,8 @@ int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_
         A.consts = prog->d_consts;
         A.n_limbs = n_limbs_dev + p0 * prog->num_limbs;
         A.sig_limbs = sig_limbs_dev + p0 * prog->num_limbs;
-        A.hash_limbs = hash_limbs_dev + p0 * 4;
+        A.hash_limbs = hash_limbs_dev + p0 * prog->aux_words;
+        A.aux_words = prog->aux_words;
         A.values = values;
         A.is_valid = is_valid_dev + p0;
         A.num_levels = prog->num_levels;
@@ -549,7 +581,8 @@ int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t
     if (!prog || !n_limbs || !sig_limbs || !hash_limbs || !advice || !is_valid) return fail(ctx, B2R_ERR_INVALID, "rsa_witness: null pointer");
     if (batch == 0) return 0;
     const size_t n = (size_t)1 << prog->k, nl = prog->num_limbs;
-    const size_t in_bytes = batch * (2 * nl + 4) * 8;
+    const size_t aw = prog->aux_words;
+    const size_t in_bytes = batch * (2 * nl + aw) * 8;
     const size_t in_al = (in_bytes + 255) & ~(size_t)255;
     // stage a bounded number of instances at a time (20 MiB of advice each at k = 17)
     const size_t per_adv = NUM_ADVICE * n * sizeof(fe_t);
@@ -563,10 +596,10 @@ int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t
     fe_t* d_adv = (fe_t*)(d + in_al + 256 + ((batch + 255) & ~(size_t)255));
     B2R_CUDA(ctx, cudaMemcpyAsync(d_n, n_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
     B2R_CUDA(ctx, cudaMemcpyAsync(d_s, sig_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
-    B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * 4 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * aw * 8, cudaMemcpyHostToDevice, ctx->stream));
     for (size_t p0 = 0; p0 < batch; p0 += G) {
         size_t g = std::min(G, batch - p0);
-        B2R_TRY(witness_run(ctx, prog, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * 4, g, blind_seed, (b2r_fr*)d_adv, d_valid + p0, p0, NUM_ADVICE * n, n));
+        B2R_TRY(witness_run(ctx, prog, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * aw, g, blind_seed, (b2r_fr*)d_adv, d_valid + p0, p0, NUM_ADVICE * n, n));
         B2R_CUDA(ctx, cudaMemcpyAsync((char*)advice + p0 * per_adv, d_adv, g * per_adv, cudaMemcpyDeviceToHost, ctx->stream));
         B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }

@@ -137,6 +137,23 @@ int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog* prog);
 int32_t b2r_prog_info(const b2r_prog* prog, uint64_t* rows_used, uint64_t* num_values,
                       uint64_t* num_levels);
 int32_t b2r_prog_num_limbs(const b2r_prog* prog); /* bits_len / 64, < 0 on error */
+/* 64-bit words per instance in the third input array of the witness / commit / prove entry points: 4 (the hash
+ * limbs) for b2r_rsa_program_build, 5 (hash limbs, then the exponent) for b2r_rsa_program_build_var, num_limbs + 1
+ * (n, then the exponent word) for b2r_bigint_program_build */
+int32_t b2r_prog_aux_words(const b2r_prog* prog);
+/* The pkcs1v15 circuit with RSAPubE::Var (reference src/lib.rs:58-63, src/chip.rs:58-70 and :99-114): the exponent is
+ * an assigned one-limb integer and RSAChip::modpow_public_key runs BigIntChip::pow_mod over exp_limb_bits of its bits
+ * (src/big_integer/chip.rs:664-696: one mul_mod, num_limbs selects and one square_mod per bit).  Input arrays as for
+ * b2r_rsa_program_build with the third one holding hash[0..3], e per instance. */
+int32_t b2r_rsa_program_build_var(b2r_ctx* ctx, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out);
+/* One BigIntInstructions method as the reference's in-file unit-test circuits drive it (src/big_integer/chip.rs:
+ * 1861-1899 refresh, 1948-1986 add_mod, 2027-2070 sub_mod, 2229-2271 pow_mod), for the methods the pkcs1v15 circuit
+ * does not call.  op: 6 = mul + refresh (both operand orders, assert_equal_fresh), 7 = add_mod, 8 = sub_mod,
+ * 9 = pow_mod with an assigned one-limb exponent.  Witness inputs: first array a, second array b, third array n
+ * followed by the exponent word (b2r_prog_aux_words = num_limbs + 1).  is_valid of the witness entry points is 0xFF
+ * where the reference would have panicked and otherwise not meaningful for these programs (it tests the last result
+ * limb against 1): compare the advice columns. */
+int32_t b2r_bigint_program_build(b2r_ctx* ctx, uint32_t op, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out);
 /* n_limbs, sig_limbs: batch x (bits_len/64) little-endian 64-bit limbs; hash_limbs:
  * batch x 4.  advice: batch x 5 x 2^k Fr, column-major per instance (HOST pointer);
  * is_valid: batch bytes (the value of the circuit's final is_valid cell).

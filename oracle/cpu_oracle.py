@@ -115,6 +115,14 @@ class RsaTable:
         return int(lib().orc_rsa_synthesize(self.h, C.c_int(self.bits_len), _p(e_le), C.c_int(e_le.size),
                                             _p(n_limbs), _p(sig_limbs), _p(hash_limbs)))
 
+    def synthesize_var(self, n_limbs, sig_limbs, hash_limbs, e: int, exp_limb_bits: int) -> int:
+        """the same circuit with RSAPubE::Var: e is an assigned one-limb integer, exp_limb_bits of its bits are used"""
+        n_limbs = np.ascontiguousarray(n_limbs, dtype=np.uint64)
+        sig_limbs = np.ascontiguousarray(sig_limbs, dtype=np.uint64)
+        hash_limbs = np.ascontiguousarray(hash_limbs, dtype=np.uint64)
+        return int(lib().orc_rsa_synthesize_var(self.h, C.c_int(self.bits_len), C.c_int(exp_limb_bits), C.c_uint64(e),
+                                                _p(n_limbs), _p(sig_limbs), _p(hash_limbs)))
+
     def advice(self) -> np.ndarray:
         out = np.empty((5, 1 << self.k, 4), dtype=np.uint64)
         lib().orc_table_advice(self.h, _p(out))
@@ -157,10 +165,11 @@ def rsa_synthesize(bits_len: int, k: int, n: int, sig: int, hashed: int, e: int 
 
 
 # ---- single BigIntChip operations (the reference's impl_bigint_test_circuit! bodies) ------------
-BIGINT_OPS = {"mul_kat": 0, "mul_mod": 1, "pow_mod_fixed_exp": 2, "add": 3, "sub": 4, "assert_in_field": 5}
+BIGINT_OPS = {"mul_kat": 0, "mul_mod": 1, "pow_mod_fixed_exp": 2, "add": 3, "sub": 4, "assert_in_field": 5,
+              "refresh": 6, "add_mod": 7, "sub_mod": 8, "pow_mod": 9}
 
 
-def bigint_op(op: str, bits_len: int, k: int, a: int, b: int = 0, n: int = 0):
+def bigint_op(op: str, bits_len: int, k: int, a: int, b: int = 0, n: int = 0, exp_limb_bits: int = 5, with_advice: bool = False):
     """runs one BigIntChip operation in a fresh table, the way the reference's unit-test circuits do
     (src/big_integer/chip.rs:1470-3264).  -> (result limbs as ints or None if the reference would have
     panicked, number of violated constraints reported by the MockProver-style checker)"""
@@ -169,13 +178,16 @@ def bigint_op(op: str, bits_len: int, k: int, a: int, b: int = 0, n: int = 0):
     nw = 2 * nl if op == "mul_kat" else nl
     aw, bw = int_to_limbs64(a, nl), int_to_limbs64(b, nl)
     nwords = int_to_limbs64(n, nw)
+    if op == "pow_mod":           # b = the exponent (one 64-bit word), the length argument carries exp_limb_bits
+        nw = exp_limb_bits
     out = np.zeros((2 * nl + 2, 4), dtype=np.uint64)
     L = lib()
     L.orc_bigint_op.restype = C.c_int
     r = L.orc_bigint_op(t.h, C.c_int(BIGINT_OPS[op]), C.c_int(bits_len), _p(aw), _p(bw), _p(nwords), C.c_int(nw), _p(out))
     bad, _ = t.check()
+    adv = t.advice() if with_advice else None
     t.free()
     if r < 0:
-        return None, bad
+        return (None, bad, adv) if with_advice else (None, bad)
     limbs = [int(out[i, 0]) | (int(out[i, 1]) << 64) | (int(out[i, 2]) << 128) | (int(out[i, 3]) << 192) for i in range(r)]
-    return limbs, bad
+    return (limbs, bad, adv) if with_advice else (limbs, bad)

@@ -518,14 +518,163 @@ static void bi_assert_in_field(rctx* c, const bigchip* ch, const bint* a, const 
     mg_assert_one(c, &lt);
 }
 
+/* ---- MainGate::to_bits / compose (third-party maingate, restated from its published semantics) --------------
+ * to_bits(composed, number_of_bits): every bit of the low number_of_bits bits of the value is assigned as a boolean
+ * cell (assign_bit), least significant first; compose() lays the terms bit_i * 2^i out like decompose() does
+ * (4 terms per row in a..d, running remainder with base -1 in e, rows chained by se_next = 1) and the composed cell
+ * is constrained equal to the input.  A value wider than number_of_bits therefore breaks the copy constraint. */
+static int mg_to_bits(rctx* c, const aval* composed, int number_of_bits, aval* bits) {
+    uint64_t cv[4]; fe_canon(&composed->v, cv);
+    fe total = fe_zero();
+    for (int i = 0; i < number_of_bits; i++) {
+        int b = (int)((cv[i >> 6] >> (i & 63)) & 1);
+        bits[i] = mg_assign_bit(c, b ? FR.one : fe_zero());
+        if (b) { uint64_t pc[4] = {0, 0, 0, 0}; pc[i >> 6] = (uint64_t)1 << (i & 63); fe p2 = fe_of_canon(pc); total = fe_add(&FR, &total, &p2); }
+    }
+    fe remaining = total;
+    aval result; memset(&result, 0, sizeof result);
+    int nchunks = (number_of_bits - 1) / 4 + 1;
+    for (int ch = 0; ch < nchunks; ch++) {
+        term t[5]; int cnt = 0;
+        fe composed_chunk = fe_zero();
+        for (int j = 4 * ch; j < 4 * ch + 4 && j < number_of_bits; j++) {
+            uint64_t pc[4] = {0, 0, 0, 0}; pc[j >> 6] = (uint64_t)1 << (j & 63);
+            fe base = fe_of_canon(pc);
+            t[cnt++] = t_assigned(&bits[j], base);
+            fe pr = fe_mul(&FR, &bits[j].v, &base); composed_chunk = fe_add(&FR, &composed_chunk, &pr);
+        }
+        while (cnt < 4) t[cnt++] = t_zero();
+        t[4] = U_SUB(remaining);
+        int is_final = ch == nchunks - 1;
+        aval o[NADV];
+        mg_apply(c, t, 5, fe_zero(), fe_zero(), fe_zero(), is_final ? fe_zero() : FE_ONE(), o);
+        if (ch == 0) result = o[4];
+        remaining = fe_sub(&FR, &remaining, &composed_chunk);
+    }
+    mg_assert_equal(c, &result, composed);
+    return number_of_bits;
+}
+
+/* RefreshAux::new (src/big_integer/mod.rs:431-482): increased_limbs_vec.  Returns its length. */
+static int refresh_aux(int limb_width, int num_limbs_l, int num_limbs_r, int* increased) {
+    static big muled[2 * MAXL + 8];
+    int nm = 0;
+    big max_limb; { big m; m.n = limb_width / 32 + 1; for (int i = 0; i < m.n; i++) m.w[i] = 0; m.w[limb_width / 32] = 1u << (limb_width % 32);
+                    big one; one.n = 1; one.w[0] = 1; big_sub(&max_limb, &m, &one); }
+    big sq; big_mul(&sq, &max_limb, &max_limb);
+    int d = num_limbs_l + num_limbs_r - 1;
+    for (int i = 0; i < d; i++) {
+        int j = num_limbs_r >= i + 1 ? 0 : i + 1 - num_limbs_r;
+        big_zero(&muled[nm]);
+        while (j < num_limbs_l && j <= i) { big_add_shifted_words(&muled[nm], sq.w, sq.n, 0); j++; }
+        nm++;
+    }
+    int cnt = 0, cur_d = 0, max_d = d;
+    while (cur_d <= max_d) {
+        if (nm <= cur_d) { big_zero(&muled[nm]); nm++; }
+        int bits = big_bits(&muled[cur_d]);
+        int num_chunks = bits % limb_width == 0 ? bits / limb_width : bits / limb_width + 1;
+        if (num_chunks == 0) return -1; /* usize underflow in the reference */
+        increased[cnt++] = num_chunks - 1;
+        /* cut muled[cur_d] into limb_width-bit chunks and add chunk j to muled[cur_d + j] */
+        big whole = muled[cur_d];
+        big_zero(&muled[cur_d]);
+        for (int j = 0; j < num_chunks; j++) {
+            uint32_t w[8] = {0}; int nw = 0;
+            for (int b = 0; b < limb_width; b++) {
+                int pbit = j * limb_width + b;
+                if ((pbit >> 5) < whole.n && ((whole.w[pbit >> 5] >> (pbit & 31)) & 1)) { w[b >> 5] |= 1u << (b & 31); if ((b >> 5) + 1 > nw) nw = (b >> 5) + 1; }
+            }
+            if (nm <= cur_d + j) { big_zero(&muled[nm]); nm++; }
+            if (nw) big_add_shifted_words(&muled[cur_d + j], w, nw, 0);
+        }
+        cur_d++;
+    }
+    return cnt;
+}
+/* chip.rs:168-233 */
+static void bi_refresh(rctx* c, const bigchip* ch, const bint* a, int num_limbs_l, int num_limbs_r, bint* out) {
+    int inc[2 * MAXL + 8];
+    int lw = ch->limb_width;
+    int num_fresh = refresh_aux(lw, num_limbs_l, num_limbs_r, inc);
+    if (num_fresh < 0 || a->n != num_limbs_l + num_limbs_r - 1 || num_fresh > MAXL) { c->failed = 1; out->n = 0; return; }
+    aval zero = mg_assign_constant(c, fe_zero());
+    aval limbs[MAXL];
+    for (int i = 0; i < a->n; i++) limbs[i] = a->l[i];
+    for (int i = a->n; i < num_fresh; i++) limbs[i] = zero;
+    aval limb_max = mg_assign_constant(c, limb_max_fe(lw));
+    for (int i = 0; i < num_fresh; i++) {
+        aval limb = limbs[i];
+        for (int j = 0; j < inc[i] + 1; j++) {
+            aval q, n; bi_div_mod_main_gate(c, &limb, &limb_max, &q, &n);
+            if (j == 0) limbs[i] = n;
+            else if (i + j >= num_fresh) { c->failed = 1; }
+            else limbs[i + j] = mg_add(c, &limbs[i + j], &n);
+            limb = q;
+        }
+        mg_assert_zero(c, &limb);
+    }
+    out->n = num_fresh;
+    for (int i = 0; i < num_fresh; i++) {
+        aval ra = range_assign(c, limbs[i].v, sublimb_bit_len(lw), lw);
+        mg_assert_equal(c, &limbs[i], &ra);
+        out->l[i] = limbs[i];
+    }
+}
+/* chip.rs:452-481 */
+static void bi_add_mod(rctx* c, const bigchip* ch, const bint* a, const bint* b, const bint* n, bint* out) {
+    bint added; bi_add(c, ch, a, b, &added);
+    bint subed; aval is_overflowed; bi_sub(c, ch, &added, n, &subed, &is_overflowed);
+    int nl = subed.n;
+    aval zero = mg_assign_constant(c, fe_zero());
+    for (int i = added.n; i < nl; i++) added.l[i] = zero;
+    aval res[MAXL];
+    for (int i = 0; i < nl; i++) res[i] = mg_select(c, &added.l[i], &subed.l[i], &is_overflowed);
+    for (int i = n->n; i < nl; i++) mg_assert_zero(c, &res[i]);
+    out->n = n->n;
+    for (int i = 0; i < n->n; i++) out->l[i] = res[i];
+}
+/* chip.rs:495-529 */
+static void bi_sub_mod(rctx* c, const bigchip* ch, const bint* a, const bint* b, const bint* n, bint* out) {
+    bint subed1, subed2; aval ov1, ov2;
+    bi_sub(c, ch, a, b, &subed1, &ov1);
+    bi_sub(c, ch, n, &subed1, &subed2, &ov2);
+    mg_assert_zero(c, &ov2);
+    int nl = subed2.n;
+    aval zero = mg_assign_constant(c, fe_zero());
+    for (int i = subed1.n; i < nl; i++) subed1.l[i] = zero;
+    aval res[MAXL];
+    for (int i = 0; i < nl; i++) res[i] = mg_select(c, &subed2.l[i], &subed1.l[i], &ov1);
+    for (int i = n->n; i < nl; i++) mg_assert_zero(c, &res[i]);
+    out->n = n->n;
+    for (int i = 0; i < n->n; i++) out->l[i] = res[i];
+}
+/* chip.rs:664-696 */
+static void bi_pow_mod(rctx* c, const bigchip* ch, const bint* a, const bint* e, const bint* n, int exp_limb_bits, bint* out) {
+    static aval e_bits[MAXL * 64];
+    int nb = 0;
+    for (int i = 0; i < e->n; i++) nb += mg_to_bits(c, &e->l[i], exp_limb_bits, e_bits + nb);
+    big one; one.n = 1; one.w[0] = 1;
+    bint acc; bi_assign_constant(c, ch, &one, ch->num_limbs, &acc);
+    bint squared = *a;
+    for (int i = 0; i < nb; i++) {
+        bint muled; bi_mul_mod(c, ch, &acc, &squared, n, &muled);
+        for (int j = 0; j < acc.n; j++) acc.l[j] = mg_select(c, &muled.l[j], &acc.l[j], &e_bits[i]);
+        bint sq = squared; bi_mul_mod(c, ch, &sq, &sq, n, &squared);
+    }
+    *out = acc;
+}
+
 /* ---- RSAChip (src/chip.rs) --------------------------------------------------------------------- */
 /* chip.rs:128-199 */
-static aval rsa_verify_pkcs1v15(rctx* c, const bigchip* ch, int bits_len, const uint8_t* e_le, int e_len,
-                                const bint* n, const bint* hashed, const bint* sig) {
+static aval rsa_verify_pkcs1v15_ex(rctx* c, const bigchip* ch, int bits_len, const uint8_t* e_le, int e_len, const bint* e_var,
+                                   int exp_limb_bits, const bint* n, const bint* hashed, const bint* sig) {
     aval is_eq = mg_assign_constant(c, FR.one);
     bigchip chip = *ch;
     bi_assert_in_field(c, &chip, sig, n);                     /* modpow_public_key, chip.rs:99-114 */
-    bint powed; bi_pow_mod_fixed_exp(c, &chip, sig, e_le, e_len, n, &powed);
+    bint powed;
+    if (e_var) bi_pow_mod(c, &chip, sig, e_var, n, exp_limb_bits, &powed);   /* AssignedRSAPubE::Var */
+    else bi_pow_mod_fixed_exp(c, &chip, sig, e_le, e_len, n, &powed);        /* AssignedRSAPubE::Fix */
     int hash_len = 4, nl = bits_len / 64;
     for (int i = 0; i < hash_len; i++) { aval e = mg_is_equal(c, &powed.l[i], &hashed->l[i]); is_eq = mg_and(c, &is_eq, &e); }
     aval p1 = mg_assign_constant(c, fe_of_u64(217300885422736416ull));
@@ -551,6 +700,10 @@ static aval rsa_verify_pkcs1v15(rctx* c, const bigchip* ch, int bits_len, const 
     aval last = mg_assign_constant(c, fe_of_u64(562949953421311ull));
     aval e5 = mg_is_equal(c, &powed.l[nl - 1], &last); is_eq = mg_and(c, &is_eq, &e5);
     return is_eq;
+}
+static aval rsa_verify_pkcs1v15(rctx* c, const bigchip* ch, int bits_len, const uint8_t* e_le, int e_len,
+                                const bint* n, const bint* hashed, const bint* sig) {
+    return rsa_verify_pkcs1v15_ex(c, ch, bits_len, e_le, e_len, NULL, 0, n, hashed, sig);
 }
 
 /* ---- table lifetime / configuration --------------------------------------------------------------- */
@@ -619,6 +772,29 @@ int orc_rsa_synthesize(orc_table* t, int bits_len, const uint8_t* e_le, int e_le
     return fe_eq(&is_valid.v, &FR.one) ? 1 : 0;
 }
 
+/* the same circuit with RSAPubE::Var (src/chip.rs:58-70, :99-114): the exponent is an assigned one-limb integer,
+ * pow_mod walks exp_limb_bits of its bits.  Region order as above; e is assigned right after n. */
+int orc_rsa_synthesize_var(orc_table* t, int bits_len, int exp_limb_bits, uint64_t e_word, const uint64_t* n_limbs,
+                           const uint64_t* sig_limbs, const uint64_t* hash_limbs) {
+    rctx* c = &t->c;
+    bigchip ch = {64, bits_len / 64};
+    int nl = bits_len / 64;
+    fe tmp[MAXL];
+    bint sig, n, e, hashed;
+    for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(sig_limbs[i]);
+    bi_assign_integer(c, &ch, tmp, nl, &sig);
+    for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(n_limbs[i]);
+    bi_assign_integer(c, &ch, tmp, nl, &n);
+    tmp[0] = fe_of_u64(e_word);
+    bi_assign_integer(c, &ch, tmp, 1, &e);
+    for (int i = 0; i < 4; i++) tmp[i] = fe_of_u64(hash_limbs[i]);
+    bi_assign_integer(c, &ch, tmp, 4, &hashed);
+    aval is_valid = rsa_verify_pkcs1v15_ex(c, &ch, bits_len, NULL, 0, &e, exp_limb_bits, &n, &hashed, &sig);
+    mg_assert_one(c, &is_valid);
+    if (c->failed) return -1;
+    return fe_eq(&is_valid.v, &FR.one) ? 1 : 0;
+}
+
 /* ---- single BigIntChip operations, as the reference's in-file test circuits drive them -------------
  * (src/big_integer/chip.rs:1470-3264: impl_bigint_test_circuit! bodies).  Integers come in as
  * little-endian 64-bit words.  out receives the result limbs as canonical 4 x u64 each.
@@ -629,6 +805,13 @@ int orc_rsa_synthesize(orc_table* t, int bits_len, const uint8_t* e_le, int e_le
  *   op 3  test_add:            c = add(a,b)                               out = nl+1 limbs
  *   op 4  test_sub:            (c, overflow) = sub(a,b)                   out = nl limbs, then overflow bit
  *   op 5  test_assert_in_field: assert_in_field(a, n)
+ *   op 6  test_refresh (chip.rs:1861-1899): ab = mul(a,b), ba = mul(b,a), both refreshed with RefreshAux(64, nl, nl),
+ *                              assert_equal_fresh                         out = 2*nl refreshed limbs of ab
+ *   op 7  test_add_mod (chip.rs:1948-1986): a,b,n = assign_integer; r = add_mod(a,b,n)   out = nl limbs
+ *   op 8  test_sub_mod (chip.rs:2027-2070): r = sub_mod(a,b,n)                            out = nl limbs
+ *   op 9  test_pow_mod (chip.rs:2229-2271): a = assign_integer, e = assign_integer([e_word]) (as RSAPubE::Var),
+ *                              n = assign_integer; r = pow_mod(a, e, n, exp_limb_bits)    out = nl limbs
+ *         (e_word = b_words[0], exp_limb_bits = n_words_len for this op)
  * returns the number of out limbs, or -1 when the reference would have panicked. */
 static void words_to_big(const uint64_t* w, int nwords, big* out) {
     out->n = 2 * nwords;
@@ -656,8 +839,9 @@ int orc_bigint_op(orc_table* t, int op, int bits_len, const uint64_t* a_words, c
     } else {
         for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(a_words[i]);
         bi_assign_integer(c, &ch, tmp, nl, &a);
-        if (op != 2) { for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(b_words[i]); bi_assign_integer(c, &ch, tmp, nl, &b); }
-        if (op == 1 || op == 2 || op == 5) { for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(n_words[i]); bi_assign_integer(c, &ch, tmp, nl, &n); }
+        if (op == 9) { tmp[0] = fe_of_u64(b_words[0]); bi_assign_integer(c, &ch, tmp, 1, &b); }
+        else if (op != 2) { for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(b_words[i]); bi_assign_integer(c, &ch, tmp, nl, &b); }
+        if (op == 1 || op == 2 || op == 5 || op >= 7) { for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(n_words[i]); bi_assign_integer(c, &ch, tmp, nl, &n); }
         if (op == 1) { bi_mul_mod(c, &ch, &a, &b, &n, &r); nout = r.n; }
         else if (op == 2) {
             uint8_t e_le[8]; for (int i = 0; i < 8; i++) e_le[i] = (uint8_t)(b_words[0] >> (8 * i));
@@ -665,6 +849,15 @@ int orc_bigint_op(orc_table* t, int op, int bits_len, const uint64_t* a_words, c
         } else if (op == 3) { bi_add(c, &ch, &a, &b, &r); nout = r.n; }
         else if (op == 4) { aval ov; bi_sub(c, &ch, &a, &b, &r, &ov); r.l[r.n] = ov; nout = r.n + 1; }
         else if (op == 5) { bi_assert_in_field(c, &ch, &a, &n); nout = 0; }
+        else if (op == 6) {
+            bint ab, ba, ba_r; bi_mul(c, &a, &b, &ab); bi_mul(c, &b, &a, &ba);
+            bi_refresh(c, &ch, &ab, nl, nl, &r); bi_refresh(c, &ch, &ba, nl, nl, &ba_r);
+            aval eq; bi_is_equal_fresh(c, &r, &ba_r, &eq); mg_assert_one(c, &eq);
+            nout = r.n;
+        }
+        else if (op == 7) { bi_add_mod(c, &ch, &a, &b, &n, &r); nout = r.n; }
+        else if (op == 8) { bi_sub_mod(c, &ch, &a, &b, &n, &r); nout = r.n; }
+        else if (op == 9) { bi_pow_mod(c, &ch, &a, &b, &n, n_words_len, &r); nout = r.n; }
         else return -2;
     }
     for (int i = 0; i < nout; i++) fe_canon(&r.l[i].v, out + 4 * i);

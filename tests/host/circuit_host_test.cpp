@@ -4,19 +4,35 @@
 // table (oracle/rsa_witness.c: orc_table_layout_digest).  No GPU, no values: layout only.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include "../../halo2-rsa_b200/csrc/circuit.hpp"
 using namespace b2r::circuit;
 
 static uint64_t mix64(uint64_t h, uint64_t v) { h ^= v; h *= 0x100000001B3ull; h ^= h >> 29; return h; }
 
+// usage: circuit_host_test <bits> <k> <e>                 pkcs1v15 circuit, fixed exponent
+//        circuit_host_test <bits> <k> var <exp_limb_bits>   pkcs1v15 circuit, RSAPubE::Var
+//        circuit_host_test <bits> <k> op <id> <exp_limb_bits>   single BigIntChip operation (BigIntTestOp ids)
+//        circuit_host_test aux <limb_width> <nl> <nr>        RefreshAux::new(...).increased_limbs_vec
 int main(int argc, char** argv) {
+    if (argc > 4 && std::string(argv[1]) == "aux") {
+        auto inc = BigIntChip::refresh_increased_limbs(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
+        printf("aux=");
+        for (size_t i = 0; i < inc.size(); i++) printf("%s%zu", i ? "," : "", inc[i]);
+        printf("\n");
+        return 0;
+    }
     unsigned bits = argc > 1 ? atoi(argv[1]) : 2048, k = argc > 2 ? atoi(argv[2]) : 17;
-    unsigned long e = argc > 3 ? strtoul(argv[3], nullptr, 10) : 65537;
+    const std::string mode = argc > 3 ? argv[3] : "65537";
+    unsigned long e = (mode == "var" || mode == "op") ? 0 : strtoul(argv[3], nullptr, 10);
     std::vector<uint8_t> e_le;
     for (unsigned long v = e; v; v >>= 8) e_le.push_back((uint8_t)v);
     try {
         RegionCtx rc((1u << k) - BLINDING_ROWS);
-        AssignedValue is_valid = record_rsa_pkcs1v15(rc, bits, e_le);
+        AssignedValue is_valid;
+        if (mode == "var") is_valid = record_rsa_pkcs1v15_var(rc, bits, argc > 4 ? atoi(argv[4]) : 17);
+        else if (mode == "op") is_valid = record_bigint_op(rc, (uint32_t)atoi(argv[4]), bits, argc > 5 ? atoi(argv[5]) : 5, nullptr);
+        else is_valid = record_rsa_pkcs1v15(rc, bits, e_le);
         uint64_t hf = 0, hc = 0, hr = 0;
         for (uint32_t r = 0; r < rc.offset; r++) {
             for (int f = 0; f < NUM_FIXED; f++) {

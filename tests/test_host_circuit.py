@@ -76,3 +76,67 @@ def test_other_exponents_and_errors(exe):
     assert rc == 2 and "error=-5" in raw
     rc, d, raw = record(exe, 2000, 17)                   # bits_len % limb_width != 0 (chip.rs:1175 assert)
     assert rc == 2 and "error=-1" in raw
+
+
+def _digest_of(table):
+    out = np.zeros(5, dtype=np.uint64)
+    CO.lib().orc_table_layout_digest(table.h, C.c_void_p(out.ctypes.data))
+    return [int(x) for x in out]
+
+
+def _assert_same_layout(d, dig):
+    rows, hf, ncop, hc, hr = dig
+    assert int(d["rows"]) == rows
+    assert int(d["fixed"]) == hf
+    assert int(d["ncopies"]) == ncop and int(d["copies"]) == hc
+    assert int(d["range"]) == hr
+
+
+@pytest.mark.parametrize("op,opid", [("refresh", 6), ("add_mod", 7), ("sub_mod", 8), ("pow_mod", 9)])
+def test_bigint_ops_layout_equals_oracle_layout(exe, op, opid):
+    """the BigIntInstructions methods the pkcs1v15 circuit does not call (refresh, add_mod, sub_mod, variable-exponent
+    pow_mod: src/big_integer/chip.rs:168-233, 452-529, 664-696) recorded by the host mirror vs the oracle's row-by-row
+    restatement of the reference's unit-test circuits"""
+    bits, k, ebits = 512, 15, 5
+    p = subprocess.run([exe, str(bits), str(k), "op", str(opid), str(ebits)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout
+    d = dict(re.findall(r"(\w+)=(\S+)", p.stdout))
+    import random
+    r = random.Random(opid)
+    n = r.getrandbits(bits) | (1 << (bits - 1)) | 1
+    a, b = r.getrandbits(bits) % n, r.getrandbits(bits) % n
+    nl = bits // 64
+    t = CO.RsaTable(bits, k)
+    L = CO.lib()
+    L.orc_bigint_op.restype = C.c_int
+    out = np.zeros((2 * nl + 2, 4), dtype=np.uint64)
+    aw = CO.int_to_limbs64(a, nl)
+    bw = CO.int_to_limbs64(17 if op == "pow_mod" else b, nl)
+    nw = CO.int_to_limbs64(n, nl)
+    rc = L.orc_bigint_op(t.h, C.c_int(opid), C.c_int(bits), CO._p(aw), CO._p(bw), CO._p(nw), C.c_int(ebits if op == "pow_mod" else nl), CO._p(out))
+    assert rc > 0 and t.check()[0] == 0
+    _assert_same_layout(d, _digest_of(t))
+    t.free()
+
+
+def test_rsa_var_layout_equals_oracle_layout(exe):
+    """pkcs1v15 circuit with RSAPubE::Var (src/chip.rs:58-70, 99-114): exponent assigned as a witness, 17 bits walked"""
+    bits, k = 1024, 18
+    p = subprocess.run([exe, str(bits), str(k), "var", "17"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout
+    d = dict(re.findall(r"(\w+)=(\S+)", p.stdout))
+    n, s, h = RF.instance(bits, 0)
+    nl = bits // 64
+    t = CO.RsaTable(bits, k)
+    assert t.synthesize_var(RF.limbs64(n, nl), RF.limbs64(s, nl), RF.limbs64(h, 4), 65537, 17) == 1
+    _assert_same_layout(d, _digest_of(t))
+    t.free()
+
+
+def test_refresh_aux_kat(exe):
+    """the reference's own KAT: RefreshAux::new(32, 1, 1).increased_limbs_vec == [1, 0] (src/big_integer/mod.rs:504-509)"""
+    p = subprocess.run([exe, "aux", "32", "1", "1"], capture_output=True, text=True)
+    assert p.stdout.strip() == "aux=1,0"
+    p = subprocess.run([exe, "aux", "64", "32", "32"], capture_output=True, text=True)
+    inc = [int(x) for x in p.stdout.strip()[4:].split(",")]
+    assert len(inc) == 64 and inc[0] == 1 and max(inc) == 2   # 2048-bit operands: every product limb spills 1-2 limbs

@@ -127,3 +127,68 @@ def test_fixture_generators_are_consistent():
     n, s, h = RF.instance(2048, 6)
     assert [int(x) for x in nl[1]] == [(n >> (64 * j)) % B for j in range(32)]
     assert pow(s, 65537, n) == RF.emsa_pkcs1_v15(h.to_bytes(32, "big"), 2048)
+
+
+def _rand(bits, seed):
+    import random
+    return random.Random(seed).getrandbits(bits)
+
+
+def test_refresh_matches_product():
+    """chip.rs:1861-1899 (test_refresh): mul(a, b) refreshed to 64-bit limbs is the integer product, limb by limb;
+    RefreshAux::new(32, 1, 1).increased_limbs_vec == [1, 0] is the reference's own KAT (mod.rs:504-509), checked in
+    tests/test_host_circuit.py against the recorder."""
+    for bits, k, seed in ((512, 14, 1), (1024, 15, 2)):
+        a, b = _rand(bits, seed), _rand(bits, seed + 100)
+        limbs, bad = CO.bigint_op("refresh", bits, k, a, b)
+        assert bad == 0 and limbs is not None
+        assert len(limbs) == 2 * (bits // 64)
+        assert all(l < (1 << 64) for l in limbs)
+        assert sum(l << (64 * i) for i, l in enumerate(limbs)) == a * b
+
+
+def test_add_mod_sub_mod_match_integers():
+    """chip.rs:1948-2110: add_mod / sub_mod for a, b < n, including the wrap-around cases.  BigIntChip::sub flags
+    a - b as overflowed when a <= b (chip.rs:327-331: the limb test is a + max - b >= 2^(64 n2), i.e. a > b), so the
+    reference returns the UNREDUCED representative n when the true result is 0: sub_mod(a, a, n) = n and
+    add_mod(a, n - a, n) = n.  The restatement reproduces that."""
+    bits, k = 1024, 15
+    n = _rand(bits, 7) | (1 << (bits - 1)) | 1
+    val = lambda limbs: sum(l << (64 * i) for i, l in enumerate(limbs))
+    cases = [(_rand(bits, 8) % n, _rand(bits, 9) % n), (n - 1, n - 1), (0, 0), (5, n - 3), (n - 3, 5), (7, 7), (9, n - 9)]
+    for a, b in cases:
+        limbs, bad = CO.bigint_op("add_mod", bits, k, a, b, n)
+        assert bad == 0 and val(limbs) == ((a + b) % n or (n if a + b else 0)), (a, b)
+        limbs, bad = CO.bigint_op("sub_mod", bits, k, a, b, n)
+        assert bad == 0 and val(limbs) == ((a - b) % n or n), (a, b)
+    # chip.rs:2111-2148 (test_bad_sub_mod) style: an operand >= n breaks a constraint or is what the reference panics on
+    limbs, bad = CO.bigint_op("sub_mod", bits, k, 1, n + 5, n)
+    assert limbs is None or bad > 0
+
+
+def test_pow_mod_variable_exponent():
+    """chip.rs:2229-2271 (test_pow_mod): 5 exponent bits, against pow(a, e, n); an exponent wider than exp_limb_bits
+    cannot be composed from its bits (to_bits) and fails"""
+    bits, k = 512, 15
+    n = _rand(bits, 21) | (1 << (bits - 1)) | 1
+    a = _rand(bits, 22) % n
+    for e in (0, 1, 2, 17, 31):
+        limbs, bad = CO.bigint_op("pow_mod", bits, k, a, e, n, exp_limb_bits=5)
+        assert bad == 0 and sum(l << (64 * i) for i, l in enumerate(limbs)) == pow(a, e, n), e
+    _, bad = CO.bigint_op("pow_mod", bits, k, a, 33, n, exp_limb_bits=5)
+    assert bad > 0
+
+
+def test_rsa_variable_exponent_circuit():
+    """src/chip.rs:372-400 shape (RSAPubE::Var): the pkcs1v15 circuit with e = 65537 given as a witness, 17 exponent bits"""
+    bits, k = 512, 17
+    n, sig, h = RF.instance(bits, 3)
+    nl = bits // 64
+    t = CO.RsaTable(bits, k)
+    assert t.synthesize_var(RF.limbs64(n, nl), RF.limbs64(sig, nl), RF.limbs64(h, 4), 65537, 17) == 1
+    assert t.check()[0] == 0
+    t.free()
+    t = CO.RsaTable(bits, k)                                  # wrong exponent: the power is not the encoded message
+    assert t.synthesize_var(RF.limbs64(n, nl), RF.limbs64(sig, nl), RF.limbs64(h, 4), 65539, 17) == 0
+    assert t.check()[0] > 0
+    t.free()
