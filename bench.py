@@ -187,9 +187,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--workload", default="rsa2048", choices=["rsa2048", "rsa4096"],
+                    help="rsa2048 = BASELINE configs[1] (the headline line, default); rsa4096 = configs[2] (RSA-4096, k = 18, batch 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global BITS, K, EXT_K, BATCH, WORKLOAD
+    if args.workload == "rsa4096":
+        BITS, K, EXT_K, BATCH = 4096, 18, 20, 32
+        WORKLOAD = WORKLOAD.replace("rsa2048_e65537_k17_batch64_per_gpu", "rsa4096_e65537_k18_batch32_per_gpu").replace("2^17", "2^18").replace("2^19", "2^20")
+    if args.batch is None:
+        args.batch = BATCH
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
