@@ -229,6 +229,188 @@ __device__ bool big_eval(const BigOp& op, const uint32_t* ids, fe_t* values, uin
     return ok;
 }
 
+// ---- the same big ops evaluated by the whole CTA -----------------------------------------------------------
+// The 19 modular multiplications of x^65537 mod n are a dependent chain, so each one is on the critical path of its
+// instance; one thread doing schoolbook multiplication and Knuth division in shared memory took 0.38 ms per
+// operation (8 ms per 64 instances: profiles/r01_ncu_full_baseline.md, k_witness_eval).  Here the CTA cooperates:
+// limbs are gathered in parallel, products are formed column-wise (thread t sums the partial products of column t
+// in 96 bits, one thread resolves the carries), and the division is a Barrett reduction with mu = floor(b^2k / n)
+// computed once per modulus and cached in shared memory (two more column-parallel products and at most two
+// correcting subtractions give the exact quotient and remainder).  Anything unusual - a limb wider than 64 bits, a
+// one-word or zero modulus, a product longer than 2k words - takes the single-thread path above, which stays the
+// definition of the result.
+struct BigScratch {
+    uint32_t *A, *B, *N, *P, *Q, *R, *MU, *NC, *T, *c0, *c1, *c2;
+    uint32_t W;
+    __device__ void carve(uint32_t* sh, uint32_t W_) {
+        W = W_;
+        uint32_t o = 7 * W + 16;  // the serial path's area comes first and is shared with it
+        auto take = [&](uint32_t n) { uint32_t* r = sh + o; o += n; return r; };
+        A = sh; B = sh + W; N = sh + 2 * W; P = sh + 3 * W;   // same places as in big_eval
+        Q = take(W + 4); R = take(W + 4); MU = take(W + 4); NC = take(W + 4); T = take(2 * W + 8);
+        c0 = take(2 * W + 8); c1 = take(2 * W + 8); c2 = take(2 * W + 8);
+    }
+    static __host__ __device__ uint32_t words(uint32_t W) { return 7 * W + 16 + 4 * (W + 4) + 4 * (2 * W + 8); }
+};
+
+// out[0 .. lx+ly) = X * Y, all threads; lx, ly >= 1
+__device__ void cta_mul(const uint32_t* X, uint32_t lx, const uint32_t* Y, uint32_t ly, uint32_t* out, BigScratch& S) {
+    const uint32_t tid = threadIdx.x, T = blockDim.x, cols = lx + ly;
+    for (uint32_t t = tid; t < cols; t += T) {
+        uint64_t lo = 0;
+        uint32_t hi = 0;
+        const uint32_t i0 = t >= ly ? t - ly + 1 : 0, i1 = t < lx ? t : lx - 1;
+        for (uint32_t i = i0; i <= i1 && t < cols - 1; i++) {
+            const uint64_t pr = (uint64_t)X[i] * Y[t - i];
+            lo += pr;
+            hi += lo < pr ? 1u : 0u;
+        }
+        S.c0[t] = (uint32_t)lo;
+        S.c1[t] = (uint32_t)(lo >> 32);
+        S.c2[t] = hi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t carry = 0;
+        for (uint32_t t = 0; t < cols; t++) {
+            carry += (uint64_t)S.c0[t] + (t >= 1 ? S.c1[t - 1] : 0) + (t >= 2 ? S.c2[t - 2] : 0);
+            out[t] = (uint32_t)carry;
+            carry >>= 32;
+        }
+    }
+    __syncthreads();
+}
+
+// returns false if this op must go through the serial path; *ok = false if the reference would have panicked
+__device__ bool big_eval_cta(const BigOp& op, const uint32_t* ids, fe_t* values, uint32_t out0, BigScratch& S, int* sh_flag, bool* ok) {
+    const uint32_t tid = threadIdx.x, T = blockDim.x, W = S.W;
+    if (op.limb_width != 64) return false;
+    const uint32_t nin = op.na + op.nb + op.nn;
+    if (2 * op.na > W || 2 * op.nb > W || 2 * op.nn > W) return false;
+    // ---- gather (limbs < 2^64 go straight to their two words)
+    if (tid == 0) *sh_flag = 0;
+    for (uint32_t i = tid; i < 3 * W; i += T) S.A[i] = 0;   // A, B, N are contiguous
+    __syncthreads();
+    for (uint32_t i = tid; i < nin; i += T) {
+        const fe_t c = Fr::from_mont(ldv(values + ids[i]));
+        if (c.l[2] | c.l[3] | c.l[4] | c.l[5] | c.l[6] | c.l[7]) atomicOr(sh_flag, 1);
+        uint32_t* dst = i < op.na ? S.A + 2 * i : (i < op.na + op.nb ? S.B + 2 * (i - op.na) : S.N + 2 * (i - op.na - op.nb));
+        dst[0] = c.l[0];
+        dst[1] = c.l[1];
+    }
+    __syncthreads();
+    const bool wide_limb = *sh_flag != 0;
+    __syncthreads();  // every thread has read the flag before it is reused below
+    if (wide_limb) return false;
+    *ok = true;
+    if (op.kind == BIG_SUB) {
+        if (tid == 0) {
+            int64_t br = 0;
+            for (uint32_t i = 0; i < W; i++) {
+                int64_t t = (int64_t)S.A[i] - S.B[i] - br;
+                S.P[i] = (uint32_t)t;
+                br = t < 0 ? 1 : 0;
+            }
+            *sh_flag = br ? 2 : 0;
+        }
+        __syncthreads();
+        const bool under = *sh_flag == 2;
+        for (uint32_t i = tid; i < op.nout; i += T) {
+            const uint64_t v = under ? 0 : ((uint64_t)S.P[2 * i] | ((uint64_t)S.P[2 * i + 1] << 32));
+            stv(values + out0 + i, fe_from_u64_dev(v));
+        }
+        *ok = !under;
+        __syncthreads();
+        return true;
+    }
+    const uint32_t la = big_len(S.A, W), lb = big_len(S.B, W), k = big_len(S.N, W);
+    if (k < 2 || la == 0 || lb == 0 || la + lb > 2 * k) return false;   // uniform: every thread reads the same shared words
+    // ---- mu for this modulus (cached)
+    if (tid == 0) *sh_flag = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < W; i += T)
+        if (S.NC[i] != S.N[i]) atomicOr(sh_flag, 1);
+    __syncthreads();
+    const bool new_modulus = *sh_flag != 0;
+    __syncthreads();
+    if (new_modulus) {
+        if (tid == 0) {
+            // mu = floor(b^(2k) / N): Knuth D on (1, 0 x 2k) by N -> k + 1 quotient words
+            uint32_t* un = S.T;   // 2k + 2 words
+            for (uint32_t i = 0; i < 2 * k + 2; i++) un[i] = 0;
+            un[2 * k] = 1;
+            for (uint32_t i = 0; i < W + 4; i++) S.MU[i] = 0;
+            big_divrem(un, 2 * k + 1, S.N, k, S.c0, S.MU, S.c1);
+            for (uint32_t i = 0; i < W; i++) S.NC[i] = S.N[i];
+        }
+        __syncthreads();
+    }
+    // ---- x = A * B
+    for (uint32_t i = tid; i < 2 * W + 2; i += T) S.P[i] = 0;
+    __syncthreads();
+    cta_mul(S.A, la, S.B, lb, S.P, S);
+    const uint32_t lp = big_len(S.P, 2 * W);
+    // ---- Barrett: q3 = floor(floor(x / b^(k-1)) * mu / b^(k+1))
+    const uint32_t lq1 = lp > k - 1 ? lp - (k - 1) : 0;
+    for (uint32_t i = tid; i < W + 4; i += T) S.Q[i] = 0;
+    __syncthreads();
+    if (lq1) {
+        const uint32_t lmu = big_len(S.MU, k + 2);
+        cta_mul(S.P + (k - 1), lq1, S.MU, lmu, S.T, S);
+        const uint32_t lt = lq1 + lmu;
+        for (uint32_t i = tid; i + (k + 1) < lt && i < W + 4; i += T) S.Q[i] = S.T[i + k + 1];
+        __syncthreads();
+    }
+    // ---- r = x - q3 * N  (mod b^(k+1)), then at most two corrections
+    const uint32_t lq3 = big_len(S.Q, k + 2);
+    for (uint32_t i = tid; i < 2 * W + 8; i += T) S.T[i] = 0;
+    __syncthreads();
+    if (lq3) cta_mul(S.Q, lq3, S.N, k, S.T, S);
+    if (tid == 0) {
+        int64_t br = 0;
+        for (uint32_t i = 0; i < k + 1; i++) {
+            int64_t t = (int64_t)S.P[i] - S.T[i] - br;
+            S.R[i] = (uint32_t)t;
+            br = t < 0 ? 1 : 0;
+        }
+        // r < 3N (Barrett): subtract N while r >= N
+        for (int iter = 0; iter < 3; iter++) {
+            bool ge = true;
+            if (S.R[k] == 0) {
+                for (int32_t i = (int32_t)k - 1; i >= 0; i--)
+                    if (S.R[i] != S.N[i]) { ge = S.R[i] > S.N[i]; break; }
+            }
+            if (!ge) break;
+            int64_t b2 = 0;
+            for (uint32_t i = 0; i < k + 1; i++) {
+                int64_t t = (int64_t)S.R[i] - (i < k ? S.N[i] : 0) - b2;
+                S.R[i] = (uint32_t)t;
+                b2 = t < 0 ? 1 : 0;
+            }
+            for (uint32_t i = 0; i < W + 4; i++)
+                if (++S.Q[i]) break;
+        }
+        // q must fit nb limbs and r must fit na limbs (asserts at chip.rs:583-584)
+        bool good = true;
+        const uint32_t lq = big_len(S.Q, W + 4), lr = big_len(S.R, k + 1);
+        if (lq > 2 * op.nb || lr > 2 * op.na) good = false;
+        *sh_flag = good ? 0 : 2;
+    }
+    __syncthreads();
+    const bool good = *sh_flag == 0;
+    for (uint32_t i = tid; i < op.nb; i += T) {
+        const uint64_t v = (uint64_t)S.Q[2 * i] | ((uint64_t)S.Q[2 * i + 1] << 32);
+        stv(values + out0 + i, fe_from_u64_dev(good ? v : 0));
+    }
+    for (uint32_t i = tid; i < op.na; i += T) {
+        const uint64_t v = (uint64_t)(2 * i < k + 1 ? S.R[2 * i] : 0) | ((uint64_t)(2 * i + 1 < k + 1 ? S.R[2 * i + 1] : 0) << 32);
+        stv(values + out0 + op.nb + i, fe_from_u64_dev(good ? v : 0));
+    }
+    *ok = good;
+    __syncthreads();
+    return true;
+}
+
 struct WitnessArgs {
     const Node* nodes;
     const LevelRange* levels;
@@ -247,10 +429,13 @@ struct WitnessArgs {
 
 __global__ void __launch_bounds__(1024) k_witness_eval(const WitnessArgs A) {
     extern __shared__ uint32_t sh_big[];
-    __shared__ int sh_err;
+    __shared__ int sh_err, sh_flag;
     const uint32_t p = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     fe_t* val = A.values + (size_t)p * A.num_values;
+    BigScratch BS;
+    BS.carve(sh_big, A.big_words);
     if (tid == 0) sh_err = 0;
+    for (uint32_t i = tid; i < A.big_words + 4; i += T) BS.NC[i] = 0;   // no modulus cached yet (a zero modulus never gets here)
     __syncthreads();
     for (uint32_t lv = 0; lv < A.num_levels; lv++) {
         const LevelRange L = A.levels[lv];
@@ -293,12 +478,18 @@ __global__ void __launch_bounds__(1024) k_witness_eval(const WitnessArgs A) {
             }
             stv(val + id, r);
         }
-        if (tid == 0) {
-            for (uint32_t bi = L.bstart; bi < L.bend; bi++) {
-                uint32_t id = A.big_nodes[bi];
-                const BigOp op = A.big_ops[A.nodes[id].a];
-                if (!big_eval(op, A.big_inputs + op.in_off, val, id + 1, sh_big, A.big_words)) sh_err = 1;
+        __syncthreads();  // the level's ordinary nodes are written before the big ops read them
+        for (uint32_t bi = L.bstart; bi < L.bend; bi++) {   // uniform across the CTA
+            const uint32_t id = A.big_nodes[bi];
+            const BigOp op = A.big_ops[A.nodes[id].a];
+            bool ok = true;
+            if (!big_eval_cta(op, A.big_inputs + op.in_off, val, id + 1, BS, &sh_flag, &ok)) {
+                __syncthreads();
+                if (tid == 0) ok = big_eval(op, A.big_inputs + op.in_off, val, id + 1, sh_big, A.big_words);
+                if (tid != 0) ok = true;
             }
+            if (!ok && tid == 0) sh_err = 1;
+            __syncthreads();
         }
         __syncthreads();
     }
@@ -530,7 +721,7 @@ int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_
     size_t G = std::max<size_t>(1, std::min<size_t>(batch, ((size_t)2 << 30) / per));
     fe_t* values = nullptr;
     B2R_TRY(scratch_get(ctx, SC_WIT, G * per, (void**)&values));
-    size_t big_smem = ((size_t)prog->max_big_words * 7 + 16) * sizeof(uint32_t);
+    size_t big_smem = (size_t)BigScratch::words(prog->max_big_words) * sizeof(uint32_t);
     if (big_smem > 48 * 1024) B2R_CUDA(ctx, cudaFuncSetAttribute(k_witness_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem));
     for (size_t p0 = 0; p0 < batch; p0 += G) {
         size_t g = std::min(G, batch - p0);
