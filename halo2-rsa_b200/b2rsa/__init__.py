@@ -147,6 +147,12 @@ class Context:
     def profile_enable(self, on: bool):
         self._ck(self.lib.b2r_profile_enable(self.h, 1 if on else 0))
 
+    def profile_read(self, name: str):
+        """-> (total device ms, launches, work units) recorded under one kernel name since the last clear"""
+        ms, cnt, units = C.c_double(), C.c_uint64(), C.c_double()
+        self._ck(self.lib.b2r_profile_read(self.h, name.encode(), C.byref(ms), C.byref(cnt), C.byref(units)))
+        return ms.value, cnt.value, units.value
+
     def profile_dump(self, clear: bool = True) -> dict:
         """-> {kernel name: (total device ms, launches)} since the last clear"""
         buf = C.create_string_buffer(1 << 16)

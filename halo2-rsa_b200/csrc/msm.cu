@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <vector>
 
 #include "ctx.hpp"
 #include "ec.cuh"
@@ -116,6 +117,46 @@ __global__ void k_precompute(const affine_t* __restrict__ bases, affine_t* __res
         }
         table[(size_t)j * n + i] = o;
     }
+}
+
+// ---- suffix sums of a base set: S_j = sum_{i >= j} P_i ---------------------------------------
+// A vector that is constant over long row runs commits as  sum_i a_i P_i = sum_j (a_j - a_{j-1}) S_j : an MSM whose
+// non-zero scalars are only the rows where the vector changes.  The grand-product columns Z of the prover are like
+// that (the ratio is 1 on every row that takes part in no copy constraint / lookup, e.g. all rows behind the circuit:
+// 43 % of the column at RSA-2048 / k = 17), so they are committed against the S_j of g_lagrange (prover.cu).
+static constexpr uint32_t SFX_CHUNK = 32;
+__global__ void __launch_bounds__(128) k_sfx_local(const affine_t* __restrict__ in, xyzz_t* __restrict__ chunk_tot, uint32_t n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t * SFX_CHUNK >= n) return;
+    const uint32_t lo = t * SFX_CHUNK, hi = min(lo + SFX_CHUNK, n);
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t i = lo; i < hi; i++) xyzz_madd(acc, in[i], false);
+    chunk_tot[t] = acc;
+}
+// exclusive suffix scan of the chunk totals; one thread (one-off per SRS, n / 32 full additions)
+__global__ void k_sfx_scan(xyzz_t* chunk_tot, uint32_t nchunks) {
+    if (blockIdx.x || threadIdx.x) return;
+    xyzz_t run = xyzz_identity();
+    for (uint32_t t = nchunks; t-- > 0;) {
+        xyzz_t v = chunk_tot[t];
+        chunk_tot[t] = run;
+        xyzz_add(run, v);
+    }
+}
+__global__ void __launch_bounds__(128) k_sfx_write(const affine_t* __restrict__ in, const xyzz_t* __restrict__ carry, xyzz_t* __restrict__ out,
+                                                   uint32_t n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t * SFX_CHUNK >= n) return;
+    const uint32_t lo = t * SFX_CHUNK, hi = min(lo + SFX_CHUNK, n);
+    xyzz_t acc = carry[t];
+    for (uint32_t i = hi; i-- > lo;) {
+        xyzz_madd(acc, in[i], false);
+        out[i] = acc;
+    }
+}
+__global__ void __launch_bounds__(128) k_normalize(const xyzz_t* __restrict__ in, affine_t* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = xyzz_to_affine(in[i]);
 }
 
 // ---- digits -----------------------------------------------------------------------------
@@ -531,7 +572,15 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     { KTimer kt(ctx, "msm_scatter", (double)G * n);
     launch_digits<true>(c, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cur, ent, key, ent_cap); }
     B2R_LAUNCH_CHECK(ctx);
-    { KTimer kt(ctx, "msm_accum_entries", (double)G * n);
+    double entries_total = (double)G * n;
+    if (ctx->profile) {   // actual number of bucket entries of this group (the sum of the last offsets), for the roofline
+        std::vector<uint32_t> last(G);
+        B2R_CUDA(ctx, cudaMemcpy2DAsync(last.data(), 4, off + B, (size_t)(B + 1) * 4, 4, G, cudaMemcpyDeviceToHost, st));
+        B2R_CUDA(ctx, cudaStreamSynchronize(st));
+        entries_total = 0;
+        for (uint32_t v : last) entries_total += v;
+    }
+    { KTimer kt(ctx, "msm_accum_entries", entries_total);
     {
         static const char* ov = getenv("B2R_MSM_VARIANT");  // tuning hook (occupancy / prefetch variants)
         const int variant = ov ? atoi(ov) : 0;
@@ -604,6 +653,62 @@ int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev
     return 0;
 }
 
+// registration from device-resident affine points (d_in must not live in the SC_MSM_B arena)
+int32_t bases_register_dev(b2r_ctx* ctx, const affine_t* d_in, size_t n, b2r_bases** out) {
+    *out = nullptr;
+    b2r_bases* bs = new b2r_bases();
+    bs->n = n;
+    bs->c = pick_window(n);
+    bs->W = (255 + bs->c - 1) / bs->c;
+    cudaError_t e = cudaMalloc(&bs->table, (size_t)bs->W * n * sizeof(affine_t));
+    if (e != cudaSuccess) {
+        delete bs;
+        return cuda_fail(ctx, e, "cudaMalloc(base table)");
+    }
+    const uint32_t SLICE = 1u << 17;
+    xyzz_t* tmp = nullptr;
+    int32_t rc = scratch_get(ctx, SC_MSM_B, (size_t)SLICE * (bs->W - 1) * sizeof(xyzz_t), (void**)&tmp);
+    if (rc) { cudaFree(bs->table); delete bs; return rc; }
+    for (size_t i0 = 0; i0 < n; i0 += SLICE) {
+        uint32_t cnt = (uint32_t)((n - i0 < SLICE) ? (n - i0) : SLICE);
+        k_precompute<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(d_in, bs->table, tmp, (uint32_t)n, (uint32_t)i0, cnt, bs->c, bs->W);
+        ctx->launches++;
+    }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(bs->table); delete bs; return cuda_fail(ctx, e, "k_precompute"); }
+    *out = bs;
+    return 0;
+}
+
+void bases_destroy(b2r_bases* bs) {
+    if (!bs) return;
+    cudaFree(bs->table);
+    delete bs;
+}
+
+// new base set S_j = sum_{i >= j} P_i of a registered set (see k_sfx_local)
+int32_t bases_register_suffix_sums(b2r_ctx* ctx, const b2r_bases* src, b2r_bases** out) {
+    *out = nullptr;
+    const uint32_t n = (uint32_t)src->n, nchunks = (n + SFX_CHUNK - 1) / SFX_CHUNK;
+    char* buf = nullptr;
+    const size_t o_x = ((size_t)nchunks * sizeof(xyzz_t) + 255) & ~(size_t)255, o_aff = o_x + (size_t)n * sizeof(xyzz_t);
+    B2R_CUDA(ctx, cudaMalloc(&buf, o_aff + (size_t)n * sizeof(affine_t)));
+    xyzz_t* tot = (xyzz_t*)buf;
+    xyzz_t* sx = (xyzz_t*)(buf + o_x);
+    affine_t* sa = (affine_t*)(buf + o_aff);
+    cudaStream_t st = ctx->stream;
+    const uint32_t gb = (nchunks + 127) / 128;
+    k_sfx_local<<<gb, 128, 0, st>>>(src->table, tot, n);
+    k_sfx_scan<<<1, 32, 0, st>>>(tot, nchunks);
+    k_sfx_write<<<gb, 128, 0, st>>>(src->table, tot, sx, n);
+    k_normalize<<<(n + 127) / 128, 128, 0, st>>>(sx, sa, n);
+    ctx->launches += 4;
+    int32_t rc = bases_register_dev(ctx, sa, n, out);  // synchronises the stream
+    cudaFree(buf);
+    return rc;
+}
+
 }  // namespace b2r
 
 using namespace b2r;
@@ -615,34 +720,10 @@ int32_t b2r_bases_register(b2r_ctx* ctx, const b2r_g1_affine* bases_host, size_t
     if (!bases_host || !out || n == 0) return fail(ctx, B2R_ERR_INVALID, "bases_register: bad argument");
     if (n > ((size_t)1 << 26)) return fail(ctx, B2R_ERR_INVALID, "bases_register: n > 2^26");
     *out = nullptr;
-    b2r_bases* bs = new b2r_bases();
-    bs->n = n;
-    bs->c = pick_window(n);
-    bs->W = (255 + bs->c - 1) / bs->c;
-    cudaError_t e = cudaMalloc(&bs->table, (size_t)bs->W * n * sizeof(affine_t));
-    if (e != cudaSuccess) {
-        delete bs;
-        return cuda_fail(ctx, e, "cudaMalloc(base table)");
-    }
     affine_t* d_in = nullptr;
-    int32_t rc = scratch_get(ctx, SC_STAGE, n * sizeof(affine_t), (void**)&d_in);
-    if (rc) { cudaFree(bs->table); delete bs; return rc; }
-    const uint32_t SLICE = 1u << 17;
-    xyzz_t* tmp = nullptr;
-    rc = scratch_get(ctx, SC_MSM_B, (size_t)SLICE * (bs->W - 1) * sizeof(xyzz_t), (void**)&tmp);
-    if (rc) { cudaFree(bs->table); delete bs; return rc; }
-    e = cudaMemcpyAsync(d_in, bases_host, n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { cudaFree(bs->table); delete bs; return cuda_fail(ctx, e, "H2D bases"); }
-    for (size_t i0 = 0; i0 < n; i0 += SLICE) {
-        uint32_t cnt = (uint32_t)((n - i0 < SLICE) ? (n - i0) : SLICE);
-        k_precompute<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(d_in, bs->table, tmp, (uint32_t)n, (uint32_t)i0, cnt, bs->c, bs->W);
-        ctx->launches++;
-    }
-    e = cudaStreamSynchronize(ctx->stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) { cudaFree(bs->table); delete bs; return cuda_fail(ctx, e, "k_precompute"); }
-    *out = bs;
-    return 0;
+    B2R_TRY(scratch_get(ctx, SC_STAGE, n * sizeof(affine_t), (void**)&d_in));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_in, bases_host, n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+    return bases_register_dev(ctx, d_in, n, out);
 }
 
 int32_t b2r_bases_download(b2r_ctx* ctx, const b2r_bases* bases, b2r_g1_affine* out_host, size_t n) {

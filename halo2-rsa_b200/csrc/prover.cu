@@ -33,6 +33,8 @@ fe_t fr_omega(uint32_t k);
 fe_t fr_zeta();
 fe_t fr_from_u64(uint64_t v);
 int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev);
+int32_t bases_register_suffix_sums(b2r_ctx* ctx, const b2r_bases* src, b2r_bases** out);
+void bases_destroy(b2r_bases* bs);
 int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
                     const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev, uint8_t* is_valid_dev,
                     size_t p_base, size_t p_stride, size_t col_stride);
@@ -58,6 +60,7 @@ __host__ __device__ inline int lookup_fsel(int l) { return l < 4 ? FX_S_COMP : F
 struct b2r_pk {
     const b2r_prog* prog = nullptr;
     const b2r_bases *g = nullptr, *gl = nullptr;
+    b2r_bases* gl_sfx = nullptr;  // suffix sums of g_lagrange: commits the run-structured grand-product columns (msm.cu k_sfx_local)
     uint32_t k = 0, ext_k = 0, n = 0, ext_n = 0, u = 0, T = 0;
     fe_t *fixed_values = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr;
     fe_t *sigma_values = nullptr, *sigma_polys = nullptr, *sigma_cosets = nullptr;
@@ -389,6 +392,17 @@ __global__ void __launch_bounds__(256) k_random_poly(fe_t* __restrict__ P, uint3
     stv(P + ((size_t)SL_RAND * B + p) * n + row, blind_value(seed, p_base + p, ST_RANDOM_POLY, row));
 }
 
+// first differences of the grand-product columns: D[z][row] = Z[row] - Z[row - 1].  Z is constant wherever the ratio is 1
+// (rows in no copy constraint / lookup, all rows behind the circuit), so D is zero there and
+// commit(Z) = sum_row D[row] * (sum_{i >= row} g_lagrange[i]) needs bucket entries only for the rows where Z moves.
+__global__ void __launch_bounds__(256) k_run_diff(const fe_t* __restrict__ Z /* [nz][n] */, fe_t* __restrict__ D, uint32_t n) {
+    const uint32_t z = blockIdx.y, row = blockIdx.x * 256 + threadIdx.x;
+    if (row >= n) return;
+    const fe_t* a = Z + (size_t)z * n;
+    const fe_t cur = ldv(a + row);
+    stv(D + (size_t)z * n + row, row ? Fr::sub(cur, ldv(a + row - 1)) : cur);
+}
+
 // ---- phase 4: quotient on the extended coset --------------------------------------------------------------------
 struct QuotArgs {
     const fe_t* E;        // [NTRANS][QB][ext_n]
@@ -652,6 +666,7 @@ static void pk_release(b2r_pk* pk) {
     cudaFree(pk->fixed_values); cudaFree(pk->fixed_polys); cudaFree(pk->fixed_cosets);
     cudaFree(pk->sigma_values); cudaFree(pk->sigma_polys); cudaFree(pk->sigma_cosets);
     cudaFree(pk->l_cosets); cudaFree(pk->range_tags); cudaFree(pk->table);
+    bases_destroy(pk->gl_sfx);
     delete pk;
 }
 
@@ -765,6 +780,7 @@ int32_t b2r_rsa_keygen(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g, c
         ctx->launches++;
         KG_CUDA(cudaStreamSynchronize(st));  // lv goes out of scope
     }
+    KG_TRY(bases_register_suffix_sums(ctx, g_lagrange, &pk->gl_sfx));
     // commitments of the verifying key
     {
         affine_t* d_cm = nullptr;
@@ -991,7 +1007,10 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
         k_random_poly<<<dim3((n + 255) / 256, B), 256, 0, st>>>(S.P, n, B, seed, p_base);
         B2R_LAUNCH_CHECK(ctx);
     }
-    B2R_TRY(msm_batch_dev(ctx, pk->gl, S.P + (size_t)SL_PZ * B * n, (size_t)NZ * B, n, S.cm));
+    // Z columns through their run structure (first differences against the suffix-sum bases); S.num is free again
+    k_run_diff<<<dim3((n + 255) / 256, NZ * B), 256, 0, st>>>(S.P + (size_t)SL_PZ * B * n, S.num, n);
+    B2R_LAUNCH_CHECK(ctx);
+    B2R_TRY(msm_batch_dev(ctx, pk->gl_sfx, S.num, (size_t)NZ * B, n, S.cm));
     B2R_TRY(msm_batch_dev(ctx, pk->g, S.P + (size_t)SL_RAND * B * n, B, n, S.cm + (size_t)NZ * B));
     B2R_TRY(fetch_points((size_t)(NZ + 1) * B));
     for (uint32_t p = 0; p < B; p++) {
