@@ -42,12 +42,12 @@ WORKLOAD = ("rsa2048_e65537_k17_batch64_per_gpu: full create_proof per instance 
 MSM_BYTES_PER_TERM = 96  # 32 B scalar + 64 B affine base
 FULL_MSM_PER_PROOF, MSM_WINDOWS = 16, 16  # grand products 7, random poly 1, h pieces 4, GWC witnesses 4; ceil(255 / 16) windows
 # dram__bytes_read.sum + dram__bytes_write.sum of k_accum_entries from the ncu --set full capture summarised in
-# profiles/r01_ncu_final.md: the launch over 409 grand-product columns (full-size scalars) moved 43.61 GB + 3.49 GB
-ACCUM_TRAFFIC_BYTES = 47.1e9
-ACCUM_TRAFFIC_VECTORS = 409
-ACCUM_TRAFFIC_SOURCE = ("ncu --set full, one k_accum_entries launch over 409 x 2^17 full-size scalars: 43.61 GB read + 3.49 GB written "
-                        "(algorithmic 5.15 GB; the rest is the 16 x 64 B table gathers per scalar of the resident-table design, "
-                        "47.6 % L2 hits) - profiles/r01_ncu_final.md")
+# profiles/r01_ncu_final.md: the launch over the 256 quotient-piece columns (full-size scalars) moved 44.52 GB + 2.32 GB
+ACCUM_TRAFFIC_BYTES = 46.8e9
+ACCUM_TRAFFIC_VECTORS = 256
+ACCUM_TRAFFIC_SOURCE = ("ncu --set full, one k_accum_entries launch over 256 x 2^17 full-size scalars: 44.52 GB read + 2.32 GB written "
+                        "(algorithmic 3.22 GB; the rest is the 16 x 64 B table gathers per scalar of the resident-table design, "
+                        "37 % L2 hits) - profiles/r01_ncu_final.md")
 
 
 def measured_peaks():
