@@ -180,11 +180,26 @@ __device__ __forceinline__ int32_t signed_digit(const fe_t& k, uint32_t& carry) 
     return (int32_t)raw;
 }
 
-template <bool SCATTER>
+// AGG: lanes of a warp that hit the same bucket are combined into one atomic (MATCH.ANY).  Columns of small or repeated
+// values need it (thousands of rows share a bucket); for scalars the caller knows to be uniformly random it is pure
+// overhead (k_digits spent 3x longer per vector on them than on run-structured columns), so those take one atomic per lane.
+template <bool SCATTER, bool AGG>
 __device__ __forceinline__ void digit_emit(int32_t d, bool live, uint32_t j, uint32_t i, uint32_t n_table, uint32_t lane, uint32_t* cnt,
                                            uint32_t* ent, uint32_t* key) {
     const bool has = live && d != 0;
     const uint32_t b = has ? (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
+    if (!AGG) {
+        if (has) {
+            if (SCATTER) {
+                const uint32_t pos = atomicAdd(&cnt[b], 1u);
+                ent[pos] = (j * n_table + i) | (d < 0 ? 0x80000000u : 0u);
+                key[pos] = b;
+            } else {
+                atomicAdd(&cnt[b], 1u);
+            }
+        }
+        return;
+    }
     // warp-aggregate lanes that hit the same bucket
     const uint32_t act = __ballot_sync(0xffffffffu, has);
     if (has) {
@@ -201,21 +216,21 @@ __device__ __forceinline__ void digit_emit(int32_t d, bool live, uint32_t j, uin
     }
 }
 
-template <bool SCATTER, int C, int J, int W>
+template <bool SCATTER, bool AGG, int C, int J, int W>
 struct DigitLoop {
     static __device__ __forceinline__ void run(const fe_t& k, uint32_t& carry, bool live, uint32_t i, uint32_t n_table, uint32_t lane,
                                                uint32_t* cnt, uint32_t* ent, uint32_t* key) {
         const int32_t d = signed_digit<C, J>(k, carry);
-        digit_emit<SCATTER>(d, live, J, i, n_table, lane, cnt, ent, key);
-        DigitLoop<SCATTER, C, J + 1, W>::run(k, carry, live, i, n_table, lane, cnt, ent, key);
+        digit_emit<SCATTER, AGG>(d, live, J, i, n_table, lane, cnt, ent, key);
+        DigitLoop<SCATTER, AGG, C, J + 1, W>::run(k, carry, live, i, n_table, lane, cnt, ent, key);
     }
 };
-template <bool SCATTER, int C, int W>
-struct DigitLoop<SCATTER, C, W, W> {
+template <bool SCATTER, bool AGG, int C, int W>
+struct DigitLoop<SCATTER, AGG, C, W, W> {
     static __device__ __forceinline__ void run(const fe_t&, uint32_t&, bool, uint32_t, uint32_t, uint32_t, uint32_t*, uint32_t*, uint32_t*) {}
 };
 
-template <bool SCATTER, int C>
+template <bool SCATTER, int C, bool AGG>
 __global__ void __launch_bounds__(256)
 k_digits(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_t B,
          uint32_t* counts /*[G][B] (count) or cursor (scatter)*/, uint32_t* entries, uint32_t* keys, size_t ent_stride) {
@@ -230,17 +245,19 @@ k_digits(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_
     uint32_t* key = SCATTER ? keys + (size_t)g * ent_stride : nullptr;
     const uint32_t lane = threadIdx.x & 31;
     uint32_t carry = 0;
-    DigitLoop<SCATTER, C, 0, W>::run(s, carry, live, i, n_table, lane, cnt, ent, key);
+    DigitLoop<SCATTER, AGG, C, 0, W>::run(s, carry, live, i, n_table, lane, cnt, ent, key);
 }
 
 template <bool SCATTER>
-static void launch_digits(uint32_t c, dim3 grid, cudaStream_t st, const fe_t* scalars, uint32_t n, uint32_t n_table, uint32_t B, uint32_t* counts,
-                          uint32_t* entries, uint32_t* keys, size_t ent_stride) {
+static void launch_digits(uint32_t c, bool agg, dim3 grid, cudaStream_t st, const fe_t* scalars, uint32_t n, uint32_t n_table, uint32_t B,
+                          uint32_t* counts, uint32_t* entries, uint32_t* keys, size_t ent_stride) {
+#define B2R_DIG(C, A) k_digits<SCATTER, C, A><<<grid, 256, 0, st>>>(scalars, n, n_table, B, counts, entries, keys, ent_stride)
     switch (c) {
-        case 10: k_digits<SCATTER, 10><<<grid, 256, 0, st>>>(scalars, n, n_table, B, counts, entries, keys, ent_stride); break;
-        case 13: k_digits<SCATTER, 13><<<grid, 256, 0, st>>>(scalars, n, n_table, B, counts, entries, keys, ent_stride); break;
-        default: k_digits<SCATTER, 16><<<grid, 256, 0, st>>>(scalars, n, n_table, B, counts, entries, keys, ent_stride); break;
+        case 10: if (agg) B2R_DIG(10, true); else B2R_DIG(10, false); break;
+        case 13: if (agg) B2R_DIG(13, true); else B2R_DIG(13, false); break;
+        default: if (agg) B2R_DIG(16, true); else B2R_DIG(16, false); break;
     }
+#undef B2R_DIG
 }
 
 // ---- single-CTA exclusive scan per vector: offsets[g][0..B], cursor[g][b] = offsets[g][b]
@@ -523,7 +540,7 @@ static uint32_t pick_window(size_t n) {
     return 16;
 }
 
-static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t G, size_t n, affine_t* out_dev) {
+static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t G, size_t n, affine_t* out_dev, bool uniform) {
     const uint32_t c = bs->c, W = bs->W, B = 1u << (c - 1);
     constexpr uint32_t L1 = MSM_L1, L2 = 16;
     const size_t ent_cap = (size_t)n * W;
@@ -564,13 +581,13 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     B2R_CUDA(ctx, cudaMemsetAsync(bk, 0, G * B * sizeof(xyzz_t), st));
     dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
     { KTimer kt(ctx, "msm_count", (double)G * n);
-    launch_digits<false>(c, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cnt, nullptr, nullptr, 0); }
+    launch_digits<false>(c, !uniform, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cnt, nullptr, nullptr, 0); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_scan");
     k_scan<<<(unsigned)G, 1024, 0, st>>>(cnt, off, cur, B); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_scatter", (double)G * n);
-    launch_digits<true>(c, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cur, ent, key, ent_cap); }
+    launch_digits<true>(c, !uniform, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cur, ent, key, ent_cap); }
     B2R_LAUNCH_CHECK(ctx);
     double entries_total = (double)G * n;
     if (ctx->profile) {   // actual number of bucket entries of this group (the sum of the last offsets), for the roofline
@@ -635,7 +652,8 @@ static size_t msm_group_bytes(const b2r_bases* bs, size_t n) {
     return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + ((size_t)B / 16 + (size_t)B / 64 + 8) * 128 + 4096 * 8;
 }
 
-int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev) {
+// `uniform`: the caller knows the non-zero scalars to be uniformly random field elements (no repeated values)
+int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev, bool uniform) {
     if (n > bs->n) return fail(ctx, B2R_ERR_INVALID, "msm: more scalars than registered bases");
     if (n == 0) {
         B2R_CUDA(ctx, cudaMemsetAsync(out_dev, 0, m * sizeof(affine_t), ctx->stream));
@@ -648,7 +666,7 @@ int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev
     if (G > 1024) G = 1024;
     for (size_t v = 0; v < m; v += G) {
         size_t g = (m - v < G) ? (m - v) : G;
-        B2R_TRY(msm_group(ctx, bs, scalars_dev + v * n, g, n, out_dev + v));
+        B2R_TRY(msm_group(ctx, bs, scalars_dev + v * n, g, n, out_dev + v, uniform));
     }
     return 0;
 }
@@ -748,7 +766,7 @@ int32_t b2r_msm_g1_batch_dev(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr*
     if (!bases || !out_dev || (!scalars_dev && n)) return fail(ctx, B2R_ERR_INVALID, "msm: null pointer");
     if (n > bases->n) return fail(ctx, B2R_ERR_INVALID, "msm: more scalars than registered bases");
     if (m == 0) return 0;
-    return msm_batch_dev(ctx, bases, (const fe_t*)scalars_dev, m, n, (affine_t*)out_dev);
+    return msm_batch_dev(ctx, bases, (const fe_t*)scalars_dev, m, n, (affine_t*)out_dev, false);
 }
 
 int32_t b2r_msm_g1_batch(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars, size_t m, size_t n,
@@ -762,7 +780,7 @@ int32_t b2r_msm_g1_batch(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* sca
     size_t sb_al = (sb + 255) & ~(size_t)255;
     B2R_TRY(scratch_get(ctx, SC_STAGE, sb_al + m * sizeof(affine_t), (void**)&d));
     if (sb) B2R_CUDA(ctx, cudaMemcpyAsync(d, scalars, sb, cudaMemcpyHostToDevice, ctx->stream));
-    B2R_TRY(msm_batch_dev(ctx, bases, (const fe_t*)d, m, n, (affine_t*)(d + sb_al)));
+    B2R_TRY(msm_batch_dev(ctx, bases, (const fe_t*)d, m, n, (affine_t*)(d + sb_al), false));
     B2R_CUDA(ctx, cudaMemcpyAsync(out, d + sb_al, m * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;

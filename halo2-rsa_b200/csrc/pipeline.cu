@@ -19,7 +19,7 @@
 namespace b2r {
 fe_t fr_omega(uint32_t k);
 fe_t fr_from_u64(uint64_t v);
-int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev);
+int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev, bool uniform);
 
 // scalar * G by double-and-add over the canonical bits (one thread per point)
 __device__ affine_t g1_mul_generator(const fe_t& scalar_mont) {
@@ -102,7 +102,7 @@ int32_t b2r_rsa_commit_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const b2r_b
     // (a) witness: 5 advice columns per instance, Lagrange basis, Montgomery form
     B2R_TRY(b2r_rsa_witness_batch_dev(ctx, prog, n_limbs_dev, sig_limbs_dev, hash_limbs_dev, batch, blind_seed, advice_dev, is_valid_dev));
     // (b) commit_lagrange of every column: one batched MSM over the resident g_lagrange table
-    B2R_TRY(msm_batch_dev(ctx, g_lagrange, (const fe_t*)advice_dev, batch * 5, n, (affine_t*)commitments_dev));
+    B2R_TRY(msm_batch_dev(ctx, g_lagrange, (const fe_t*)advice_dev, batch * 5, n, (affine_t*)commitments_dev, false));
     if (ext_dev) {
         // lagrange_to_coeff in place, then coeff_to_extended into the extended-domain buffer
         B2R_TRY(b2r_intt_fr_batch_dev(ctx, advice_dev, batch * 5, k));

@@ -32,7 +32,7 @@ namespace b2r {
 fe_t fr_omega(uint32_t k);
 fe_t fr_zeta();
 fe_t fr_from_u64(uint64_t v);
-int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev);
+int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev, bool uniform);
 int32_t bases_register_suffix_sums(b2r_ctx* ctx, const b2r_bases* src, b2r_bases** out);
 void bases_destroy(b2r_bases* bs);
 int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
@@ -785,8 +785,8 @@ int32_t b2r_rsa_keygen(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g, c
     {
         affine_t* d_cm = nullptr;
         KG_TRY(scratch_get(ctx, SC_STAGE, 64 * sizeof(affine_t), (void**)&d_cm));
-        KG_TRY(msm_batch_dev(ctx, g_lagrange, pk->fixed_values, NFIXED, n, d_cm));
-        KG_TRY(msm_batch_dev(ctx, g_lagrange, pk->sigma_values, NPERM, n, d_cm + NFIXED));
+        KG_TRY(msm_batch_dev(ctx, g_lagrange, pk->fixed_values, NFIXED, n, d_cm, false));
+        KG_TRY(msm_batch_dev(ctx, g_lagrange, pk->sigma_values, NPERM, n, d_cm + NFIXED, false));
         pk->fixed_commitments.resize(NFIXED);
         pk->sigma_commitments.resize(NPERM);
         KG_CUDA(cudaMemcpyAsync(pk->fixed_commitments.data(), d_cm, NFIXED * sizeof(affine_t), cudaMemcpyDeviceToHost, st));
@@ -956,7 +956,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
 
     // ---- phase 1: witness + advice commitments
     B2R_TRY(witness_run(ctx, pk->prog, d_n, d_s, d_h, B, seed, (b2r_fr*)S.P, S.valid, p_base, /*p_stride=*/n, /*col_stride=*/(size_t)B * n));
-    B2R_TRY(msm_batch_dev(ctx, pk->gl, S.P + (size_t)SL_ADV * B * n, (size_t)NADV * B, n, S.cm));
+    B2R_TRY(msm_batch_dev(ctx, pk->gl, S.P + (size_t)SL_ADV * B * n, (size_t)NADV * B, n, S.cm, false));
     B2R_CUDA(ctx, cudaMemcpyAsync(valid.data(), S.valid, B, cudaMemcpyDeviceToHost, st));
     B2R_TRY(fetch_points((size_t)NADV * B));
     for (uint32_t p = 0; p < B; p++) {
@@ -977,7 +977,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
         k_lookup_fill<<<dim3((n + 255) / 256, NLOOK, B), 256, 0, st>>>(S.P, S.plans, S.sorted_cv, T, n, u, B, seed, p_base);
         B2R_LAUNCH_CHECK(ctx);
     }
-    B2R_TRY(msm_batch_dev(ctx, pk->gl, S.P + (size_t)SL_LA * B * n, (size_t)2 * NLOOK * B, n, S.cm));
+    B2R_TRY(msm_batch_dev(ctx, pk->gl, S.P + (size_t)SL_LA * B * n, (size_t)2 * NLOOK * B, n, S.cm, false));
     B2R_CUDA(ctx, cudaMemcpyAsync(err.data(), S.err, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     B2R_TRY(fetch_points((size_t)2 * NLOOK * B));
     for (uint32_t p = 0; p < B; p++) {
@@ -1010,8 +1010,8 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     // Z columns through their run structure (first differences against the suffix-sum bases); S.num is free again
     k_run_diff<<<dim3((n + 255) / 256, NZ * B), 256, 0, st>>>(S.P + (size_t)SL_PZ * B * n, S.num, n);
     B2R_LAUNCH_CHECK(ctx);
-    B2R_TRY(msm_batch_dev(ctx, pk->gl_sfx, S.num, (size_t)NZ * B, n, S.cm));
-    B2R_TRY(msm_batch_dev(ctx, pk->g, S.P + (size_t)SL_RAND * B * n, B, n, S.cm + (size_t)NZ * B));
+    B2R_TRY(msm_batch_dev(ctx, pk->gl_sfx, S.num, (size_t)NZ * B, n, S.cm, true));   // non-zero differences of a grand product: uniform
+    B2R_TRY(msm_batch_dev(ctx, pk->g, S.P + (size_t)SL_RAND * B * n, B, n, S.cm + (size_t)NZ * B, true));
     B2R_TRY(fetch_points((size_t)(NZ + 1) * B));
     for (uint32_t p = 0; p < B; p++) {
         for (int j = 0; j < NZ + 1; j++) tr[p].write_point(cm[(size_t)j * B + p].x, cm[(size_t)j * B + p].y);
@@ -1038,7 +1038,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
         B2R_CUDA(ctx, cudaMemcpy2DAsync(S.hbuf + (size_t)q0 * QD * n, (size_t)QD * n * 32, S.hext, (size_t)ext_n * 32, (size_t)QD * n * 32, qb,
                                         cudaMemcpyDeviceToDevice, st));
     }
-    B2R_TRY(msm_batch_dev(ctx, pk->g, S.hbuf, (size_t)QD * B, n, S.cm));
+    B2R_TRY(msm_batch_dev(ctx, pk->g, S.hbuf, (size_t)QD * B, n, S.cm, true));
     B2R_TRY(fetch_points((size_t)QD * B));
     std::vector<fe_t> points((size_t)B * NPOINTS), scal((size_t)B * NPOINTS * MAXTERMS, Fr::zero()), xn(B);
     {
@@ -1099,7 +1099,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     B2R_LAUNCH_CHECK(ctx);
     k_kate<<<dim3(NPOINTS, B), 256, 0, st>>>(S.lc, S.points, n, S.wq); }
     B2R_LAUNCH_CHECK(ctx);
-    B2R_TRY(msm_batch_dev(ctx, pk->g, S.wq, (size_t)NPOINTS * B, n, S.cm));
+    B2R_TRY(msm_batch_dev(ctx, pk->g, S.wq, (size_t)NPOINTS * B, n, S.cm, true));
     B2R_TRY(fetch_points((size_t)NPOINTS * B));
     for (uint32_t p = 0; p < B; p++) {
         for (int g = 0; g < NPOINTS; g++) tr[p].write_point(cm[(size_t)p * NPOINTS + g].x, cm[(size_t)p * NPOINTS + g].y);
