@@ -40,6 +40,8 @@ struct NttPassArgs {
     fe_t* y;
     const fe_t* tw;       // omega^e, e < n/2
     uint64_t in_stride;   // elements between consecutive vectors of the batch (input)
+    uint64_t in_stride2;  // two-level input addressing: vector v starts at (v / in_inner) * in_stride2 + (v % in_inner) * in_stride
+    uint32_t in_inner;    // (0 = flat: v * in_stride)
     uint64_t out_stride;  // same for output
     uint32_t in_len;      // valid input elements per vector (rest read as zero)
     uint32_t log_n;
@@ -96,7 +98,8 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
     const uint32_t log_c = A.log_c, C = 1u << log_c, cmask = C - 1;
     const uint32_t log_cols = A.log_n - S;  // columns = n / R
     const uint32_t c0 = blockIdx.x << log_c;
-    const fe_t* x = A.x + (uint64_t)blockIdx.y * A.in_stride;
+    const fe_t* x = A.in_inner ? A.x + (uint64_t)(blockIdx.y / A.in_inner) * A.in_stride2 + (uint64_t)(blockIdx.y % A.in_inner) * A.in_stride
+                               : A.x + (uint64_t)blockIdx.y * A.in_stride;
     fe_t* y = A.y + (uint64_t)blockIdx.y * A.out_stride;
     const uint32_t smask = (1u << A.log_s) - 1;
 
@@ -260,7 +263,8 @@ enum NttMode { MODE_PLAIN = 0, MODE_INV = 1, MODE_COSET_FWD = 2, MODE_COSET_INV 
 // Runs the passes.  in: `batch` vectors of in_len valid elements (stride in_stride);
 // out: 2^log_n elements each (stride out_stride).  `in` may equal `out` (in place).
 static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_t in_len, fe_t* out,
-                       uint64_t out_stride, size_t batch, const fe_t& omega, uint32_t log_n, int mode) {
+                       uint64_t out_stride, size_t batch, const fe_t& omega, uint32_t log_n, int mode, uint32_t in_inner = 0,
+                       uint64_t in_stride2 = 0) {
     if (log_n > 27) return fail(ctx, B2R_ERR_INVALID, "ntt: log_n > 27");
     if (batch == 0) return 0;
     if (batch > 65535) return fail(ctx, B2R_ERR_INVALID, "ntt: batch > 65535");
@@ -312,6 +316,8 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         A.y = dst;
         A.tw = tw;
         A.in_stride = src_stride;
+        A.in_inner = p == 0 ? in_inner : 0;   // only the first pass reads the caller's layout
+        A.in_stride2 = in_stride2;
         A.out_stride = dst_stride;
         A.in_len = src_len;
         A.log_n = log_n;
@@ -384,6 +390,14 @@ static int32_t ntt_host(b2r_ctx* ctx, const b2r_fr* in, uint32_t in_len, b2r_fr*
     B2R_CUDA(ctx, cudaMemcpyAsync(out, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+// coeff_to_extended for `outer` x `inner` vectors in one batched launch per pass: vector (o, i) starts at
+// coeffs + o * outer_stride + i * 2^k (elements); outputs are contiguous, (o * inner + i) * 2^ext_k
+int32_t coset_ntt_grouped_dev(b2r_ctx* ctx, const fe_t* coeffs, size_t outer, uint64_t outer_stride, size_t inner, uint32_t k, uint32_t ext_k,
+                              fe_t* out) {
+    return ntt_run(ctx, coeffs, 1ull << k, 1u << k, out, 1ull << ext_k, outer * inner, fr_omega(ext_k), ext_k, MODE_COSET_FWD, (uint32_t)inner,
+                   outer_stride);
 }
 
 }  // namespace b2r

@@ -34,6 +34,8 @@ fe_t fr_zeta();
 fe_t fr_from_u64(uint64_t v);
 int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev, bool uniform);
 int32_t bases_register_suffix_sums(b2r_ctx* ctx, const b2r_bases* src, b2r_bases** out);
+int32_t coset_ntt_grouped_dev(b2r_ctx* ctx, const fe_t* coeffs, size_t outer, uint64_t outer_stride, size_t inner, uint32_t k, uint32_t ext_k,
+                              fe_t* out);
 void bases_destroy(b2r_bases* bs);
 int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
                     const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev, uint8_t* is_valid_dev,
@@ -1026,8 +1028,13 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     B2R_TRY(b2r_intt_fr_batch_dev(ctx, (b2r_fr*)S.P, (size_t)NTRANS * B, k));
     for (uint32_t q0 = 0; q0 < B; q0 += QB) {
         const uint32_t qb = std::min(QB, B - q0);
-        for (int s = 0; s < NTRANS; s++)
-            B2R_TRY(b2r_coset_ntt_fr_batch_dev(ctx, (b2r_fr*)(S.P + ((size_t)s * B + q0) * n), qb, k, pk->ext_k, (b2r_fr*)(S.E + (size_t)s * QB * ext_n)));
+        // all 22 columns of the sub-batch in one launch per pass (slot-major arena: slot s of proof q0 + j at (s * B + q0 + j) * n)
+        if (qb == QB) {
+            B2R_TRY(coset_ntt_grouped_dev(ctx, S.P + (size_t)q0 * n, NTRANS, (uint64_t)B * n, qb, k, pk->ext_k, S.E));
+        } else {
+            for (int s = 0; s < NTRANS; s++)
+                B2R_TRY(b2r_coset_ntt_fr_batch_dev(ctx, (b2r_fr*)(S.P + ((size_t)s * B + q0) * n), qb, k, pk->ext_k, (b2r_fr*)(S.E + (size_t)s * QB * ext_n)));
+        }
         QuotArgs A;
         A.E = S.E; A.fixed_c = pk->fixed_cosets; A.sigma_c = pk->sigma_cosets; A.l_c = pk->l_cosets; A.tw_ext = tw_ext;
         A.chal = S.chal + (size_t)q0 * 8; A.ypow = S.ypow + (size_t)q0 * NCONS; A.h = S.hext; A.ext_n = ext_n; A.step = ext_n / n; A.QB = QB;
