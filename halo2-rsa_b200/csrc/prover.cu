@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <thread>
 #include <cstring>
 #include <vector>
 
@@ -893,11 +894,32 @@ static void build_plans(EvalPlan& ep, LincombPlan& lp) {
     add_q(0, 0, SL_RAND);
 }
 
+// The per-proof host work between the GPU phases (Blake2b transcripts, Montgomery conversions, challenge powers) is
+// independent across proofs: spread it over a few host threads so that the GPU does not idle behind one core
+// (about 0.1 ms of host field arithmetic per proof and step).
+template <class F>
+static void parallel_for_proofs(uint32_t count, F body) {
+    uint32_t nt = std::min<uint32_t>(8, std::max<uint32_t>(1, std::thread::hardware_concurrency()));
+    nt = std::min<uint32_t>(nt, std::max<uint32_t>(1, count / 4));
+    if (nt <= 1) {
+        for (uint32_t p = 0; p < count; p++) body(p);
+        return;
+    }
+    std::vector<std::thread> th;
+    auto range = [&](uint32_t t) {
+        const uint32_t lo = (uint64_t)count * t / nt, hi = (uint64_t)count * (t + 1) / nt;
+        for (uint32_t p = lo; p < hi; p++) body(p);
+    };
+    for (uint32_t t = 1; t < nt; t++) th.emplace_back(range, t);
+    range(0);
+    for (auto& x : th) x.join();
+}
+
 // one group of at most `B` proofs, inputs already on the device
 static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, const uint64_t* d_s, const uint64_t* d_h, uint32_t B,
                            uint64_t seed, uint32_t p_base, uint8_t* proofs_host, uint8_t* status_host, size_t proof_bytes) {
     const uint32_t n = pk->n, ext_n = pk->ext_n, u = pk->u, k = pk->k, T = pk->T;
-    const uint32_t QB = std::min<uint32_t>(B, 8);
+    const uint32_t QB = std::min<uint32_t>(B, 16);
     const uint32_t nch = n / CH;
     cudaStream_t st = ctx->stream;
     const DevConsts C = make_consts(pk);
@@ -961,11 +983,11 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     B2R_TRY(msm_batch_dev(ctx, pk->gl, S.P + (size_t)SL_ADV * B * n, (size_t)NADV * B, n, S.cm, false));
     B2R_CUDA(ctx, cudaMemcpyAsync(valid.data(), S.valid, B, cudaMemcpyDeviceToHost, st));
     B2R_TRY(fetch_points((size_t)NADV * B));
-    for (uint32_t p = 0; p < B; p++) {
+    parallel_for_proofs(B, [&](uint32_t p) {
         tr[p].common_scalar(pk->transcript_repr);
         for (int c = 0; c < NADV; c++) tr[p].write_point(cm[(size_t)c * B + p].x, cm[(size_t)c * B + p].y);
         chal[(size_t)p * 8 + 0] = tr[p].squeeze();  // theta
-    }
+    });
     B2R_TRY(push_chal());
     // ---- phase 2: lookups
     {
@@ -982,11 +1004,11 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     B2R_TRY(msm_batch_dev(ctx, pk->gl, S.P + (size_t)SL_LA * B * n, (size_t)2 * NLOOK * B, n, S.cm, false));
     B2R_CUDA(ctx, cudaMemcpyAsync(err.data(), S.err, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     B2R_TRY(fetch_points((size_t)2 * NLOOK * B));
-    for (uint32_t p = 0; p < B; p++) {
+    parallel_for_proofs(B, [&](uint32_t p) {
         for (int j = 0; j < 2 * NLOOK; j++) tr[p].write_point(cm[(size_t)j * B + p].x, cm[(size_t)j * B + p].y);
         chal[(size_t)p * 8 + 1] = tr[p].squeeze();  // beta
         chal[(size_t)p * 8 + 2] = tr[p].squeeze();  // gamma
-    }
+    });
     B2R_TRY(push_chal());
     // ---- phase 3: grand products + random polynomial
     {
@@ -1015,13 +1037,13 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     B2R_TRY(msm_batch_dev(ctx, pk->gl_sfx, S.num, (size_t)NZ * B, n, S.cm, true));   // non-zero differences of a grand product: uniform
     B2R_TRY(msm_batch_dev(ctx, pk->g, S.P + (size_t)SL_RAND * B * n, B, n, S.cm + (size_t)NZ * B, true));
     B2R_TRY(fetch_points((size_t)(NZ + 1) * B));
-    for (uint32_t p = 0; p < B; p++) {
+    parallel_for_proofs(B, [&](uint32_t p) {
         for (int j = 0; j < NZ + 1; j++) tr[p].write_point(cm[(size_t)j * B + p].x, cm[(size_t)j * B + p].y);
         chal[(size_t)p * 8 + 3] = tr[p].squeeze();  // y
         fe_t* yp = ypow.data() + (size_t)p * NCONS;   // y^(NCONS-1-k): the weight of constraint k in h
         yp[NCONS - 1] = Fr::one();
         for (int k = NCONS - 2; k >= 0; k--) yp[k] = Fr::mul(yp[k + 1], chal[(size_t)p * 8 + 3]);
-    }
+    });
     B2R_TRY(push_chal());
     B2R_CUDA(ctx, cudaMemcpyAsync(S.ypow, ypow.data(), ypow.size() * 32, cudaMemcpyHostToDevice, st));
     // ---- phase 4: coefficient forms, extended coset, quotient
@@ -1051,7 +1073,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     {
         const fe_t omega = fr_omega(k), omega_inv = Fr::inv(omega);
         const fe_t w_last = fr_pow_host(omega_inv, BF + 1);
-        for (uint32_t p = 0; p < B; p++) {
+        parallel_for_proofs(B, [&](uint32_t p) {
             for (int j = 0; j < QD; j++) tr[p].write_point(cm[(size_t)p * QD + j].x, cm[(size_t)p * QD + j].y);
             const fe_t x = tr[p].squeeze();
             chal[(size_t)p * 8 + 4] = x;
@@ -1060,7 +1082,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
             points[(size_t)p * NPOINTS + 2] = Fr::mul(x, w_last);
             points[(size_t)p * NPOINTS + 3] = Fr::mul(x, omega_inv);
             xn[p] = fr_pow_host(x, n);
-        }
+        });
     }
     B2R_CUDA(ctx, cudaMemcpyAsync(S.points, points.data(), points.size() * 32, cudaMemcpyHostToDevice, st));
     // ---- phase 5: evaluations
@@ -1072,7 +1094,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     std::vector<fe_t> evals((size_t)B * NEVAL);
     B2R_CUDA(ctx, cudaMemcpyAsync(evals.data(), S.evals, evals.size() * 32, cudaMemcpyDeviceToHost, st));
     B2R_CUDA(ctx, cudaStreamSynchronize(st));
-    for (uint32_t p = 0; p < B; p++) {
+    parallel_for_proofs(B, [&](uint32_t p) {
         for (int e = 0; e < NEVAL; e++) tr[p].write_scalar(evals[(size_t)p * NEVAL + e]);
         const fe_t v = tr[p].squeeze();
         // scalars of the GWC linear combinations: term j of m gets v^(m-1-j); the QD h pieces share one v power
@@ -1098,7 +1120,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
                 scal[((size_t)p * NPOINTS + g) * MAXTERMS + j] = s;
             }
         }
-    }
+    });
     B2R_CUDA(ctx, cudaMemcpyAsync(S.scal, scal.data(), scal.size() * 32, cudaMemcpyHostToDevice, st));
     // ---- phase 6: GWC witnesses
     { KTimer kt(ctx, "multiopen", (double)B);
