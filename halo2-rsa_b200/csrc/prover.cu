@@ -1001,11 +1001,29 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
         k_lookup_fill<<<dim3((n + 255) / 256, NLOOK, B), 256, 0, st>>>(S.P, S.plans, S.sorted_cv, T, n, u, B, seed, p_base);
         B2R_LAUNCH_CHECK(ctx);
     }
-    B2R_TRY(msm_batch_dev(ctx, pk->gl, S.P + (size_t)SL_LA * B * n, (size_t)2 * NLOOK * B, n, S.cm, false));
+    // A' is sorted, i.e. constant over at most T + 1 runs: commit it through its first differences against the suffix-sum
+    // bases like the grand products (a few hundred non-zero scalars instead of every looked-up row); S' is non-zero only
+    // at run starts and is committed directly.  S.num .. S.den (contiguous, free until phase 3) hold D(A'_l) then S'_l.
+    {
+        fe_t* DA = S.num;
+        fe_t* SS = S.num + (size_t)NLOOK * B * n;
+        if (S.den != S.num + (size_t)NZ * B * n) return fail(ctx, B2R_ERR_INVALID, "prove: scratch layout");
+        for (int l = 0; l < NLOOK; l++) {
+            k_run_diff<<<dim3((n + 255) / 256, B), 256, 0, st>>>(S.P + (size_t)(SL_LA + 2 * l) * B * n, DA + (size_t)l * B * n, n);
+            B2R_LAUNCH_CHECK(ctx);
+        }
+        B2R_CUDA(ctx, cudaMemcpy2DAsync(SS, (size_t)B * n * 32, S.P + (size_t)(SL_LA + 1) * B * n, (size_t)2 * B * n * 32, (size_t)B * n * 32, NLOOK,
+                                        cudaMemcpyDeviceToDevice, st));
+        B2R_TRY(msm_batch_dev(ctx, pk->gl_sfx, DA, (size_t)NLOOK * B, n, S.cm, false));
+        B2R_TRY(msm_batch_dev(ctx, pk->gl, SS, (size_t)NLOOK * B, n, S.cm + (size_t)NLOOK * B, false));
+    }
     B2R_CUDA(ctx, cudaMemcpyAsync(err.data(), S.err, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     B2R_TRY(fetch_points((size_t)2 * NLOOK * B));
     parallel_for_proofs(B, [&](uint32_t p) {
-        for (int j = 0; j < 2 * NLOOK; j++) tr[p].write_point(cm[(size_t)j * B + p].x, cm[(size_t)j * B + p].y);
+        for (int j = 0; j < 2 * NLOOK; j++) {   // halo2 writes A'_l, S'_l per lookup
+            const affine_t& c = cm[((size_t)(j & 1) * NLOOK + (j >> 1)) * B + p];
+            tr[p].write_point(c.x, c.y);
+        }
         chal[(size_t)p * 8 + 1] = tr[p].squeeze();  // beta
         chal[(size_t)p * 8 + 2] = tr[p].squeeze();  // gamma
     });
