@@ -76,7 +76,7 @@ __device__ __forceinline__ void st_fe(fe_t* p, const fe_t& v) {
 }
 
 template <int S>
-__global__ void __launch_bounds__(256) k_ntt_pass(const NttPassArgs A) {
+__global__ void __launch_bounds__(256, 4) k_ntt_pass(const NttPassArgs A) {
     constexpr uint32_t R = 1u << S;
     // shared tile, split into the low and the high 16 bytes of every element: a warp's 128-bit accesses then touch
     // consecutive banks (32-byte elements accessed whole are a 2-way bank conflict on every load and store)
