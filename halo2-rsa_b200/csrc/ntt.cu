@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(256, 4) k_ntt_pass(const NttPassArgs A) {
             const fe_t u0 = Fr::add(a0, a2), u1 = Fr::add(a1, a3);
             fe_t d0 = Fr::sub(a0, a2), d1 = Fr::sub(a1, a3);
             if (ea) d0 = Fr::mul(d0, ld_fe_nc(A.tw + ea));
-            d1 = Fr::mul(d1, ld_fe_nc(A.tw + eb));
+            // zero-padded first pass (coeff_to_extended: 3/4 of the rows are zero): a1 = a3 = 0 in the first round, 0 * w = 0
+            if (!Fr::is_zero(d1)) d1 = Fr::mul(d1, ld_fe_nc(A.tw + eb));
             const fe_t wc = ld_fe_nc(A.tw + ec);
             sts(i0, Fr::add(u0, u1));
             sts(i0 + 2 * st, Fr::add(d0, d1));
