@@ -260,6 +260,130 @@ static void launch_digits(uint32_t c, bool agg, dim3 grid, cudaStream_t st, cons
 #undef B2R_DIG
 }
 
+// digit loop of k_bin_scatter: window J of the scalar -> packed entry (table index | sign << idx_bits | low 8 bucket bits
+// << (idx_bits + 1)) and its rank among the CTA's entries of the same high-7-bit bin
+template <int C, int J, int W>
+struct DigitLoopBins {
+    static __device__ __forceinline__ void run(const fe_t& k, uint32_t& carry, uint32_t i, uint32_t n_table, uint32_t idx_bits, uint32_t* hist,
+                                               uint32_t* packed, uint32_t* where) {
+        const int32_t d = signed_digit<C, J>(k, carry);
+        if (d != 0) {
+            const uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1, hi = b >> 8, lo = b & 255u;
+            packed[J] = ((uint32_t)J * n_table + i) | ((d < 0 ? 1u : 0u) << idx_bits) | (lo << (idx_bits + 1));
+            where[J] = (hi << 16) | atomicAdd(&hist[hi], 1u);
+        } else {
+            packed[J] = 0;
+            where[J] = 0xffffffffu;
+        }
+        DigitLoopBins<C, J + 1, W>::run(k, carry, i, n_table, idx_bits, hist, packed, where);
+    }
+};
+template <int C, int W>
+struct DigitLoopBins<C, W, W> {
+    static __device__ __forceinline__ void run(const fe_t&, uint32_t&, uint32_t, uint32_t, uint32_t, uint32_t*, uint32_t*, uint32_t*) {}
+};
+
+// ---- binned counting sort for vectors the caller declares uniform (c = 16) ---------------------------------------
+// The per-entry global atomics and scattered 4-byte stores of k_digits are what bound it on dense random scalars
+// (56 us per 2^17 vector against 350 us of accumulation).  Uniform digits make every group of 256 buckets receive
+// ~16 K entries, so the sort is done in two coalesced steps: k_bin_scatter partitions the entries by the high 7 bits of
+// the bucket (shared-memory ranks, one global reservation per CTA and bin, runs of ~32 entries written together into
+// fixed-capacity bins), k_bin_sort finishes each bin in shared memory by the low 8 bits and writes the final sorted
+// list, the keys and the bucket offsets.  A bin that overflows its capacity raises a flag and the group is redone by
+// the general kernels.
+static constexpr uint32_t BIN_HI = 128, BIN_LO = 256, BIN_CAP = 20480, BIN_SORT_T = 512;
+
+template <int C>
+__global__ void __launch_bounds__(256)
+k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_t idx_bits, uint32_t* __restrict__ bin_fill /*[G][128]*/,
+              uint32_t* __restrict__ bins /*[G][128][CAP]*/, uint32_t* __restrict__ flags) {
+    constexpr int W = (255 + C - 1) / C;
+    __shared__ uint32_t hist[BIN_HI], base[BIN_HI];
+    const uint32_t g = blockIdx.y, tid = threadIdx.x, i = blockIdx.x * 256 + tid;
+    if (tid < BIN_HI) hist[tid] = 0;
+    __syncthreads();
+    fe_t s = Fr::zero();
+    if (i < n) s = Fr::from_mont(ldg_fe(scalars + (size_t)g * n + i));
+    uint32_t packed[W], where[W];   // where = hi << 16 | rank inside the CTA's share of the bin; 0xffffffff = no entry
+    uint32_t carry = 0;
+    DigitLoopBins<C, 0, W>::run(s, carry, i, n_table, idx_bits, hist, packed, where);
+    __syncthreads();
+    if (tid < BIN_HI) base[tid] = hist[tid] ? atomicAdd(&bin_fill[(size_t)g * BIN_HI + tid], hist[tid]) : 0;
+    __syncthreads();
+    uint32_t* mine = bins + (size_t)g * BIN_HI * BIN_CAP;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        if (where[j] == 0xffffffffu) continue;
+        const uint32_t hi = where[j] >> 16, pos = base[hi] + (where[j] & 0xffffu);
+        if (pos < BIN_CAP) mine[(size_t)hi * BIN_CAP + pos] = packed[j];
+        else atomicOr(flags + g, 1u);
+    }
+}
+
+// exclusive scan of the 128 bin sizes of every vector -> bin_base[g][0..128] (bin_base[g][128] = number of entries)
+__global__ void __launch_bounds__(BIN_HI) k_bin_prefix(const uint32_t* __restrict__ bin_fill, uint32_t* __restrict__ bin_base, uint32_t* __restrict__ off,
+                                                       uint32_t B) {
+    __shared__ uint32_t sh[BIN_HI];
+    const uint32_t g = blockIdx.x, t = threadIdx.x;
+    const uint32_t v = min(bin_fill[(size_t)g * BIN_HI + t], BIN_CAP);
+    sh[t] = v;
+    __syncthreads();
+    for (uint32_t d = 1; d < BIN_HI; d <<= 1) {
+        const uint32_t o = t >= d ? sh[t - d] : 0;
+        __syncthreads();
+        sh[t] += o;
+        __syncthreads();
+    }
+    bin_base[(size_t)g * (BIN_HI + 1) + t] = sh[t] - v;
+    if (t == BIN_HI - 1) {
+        bin_base[(size_t)g * (BIN_HI + 1) + BIN_HI] = sh[t];
+        off[(size_t)g * (B + 1) + B] = sh[t];
+    }
+}
+
+__global__ void __launch_bounds__(BIN_SORT_T)
+k_bin_sort(const uint32_t* __restrict__ bins, const uint32_t* __restrict__ bin_fill, const uint32_t* __restrict__ bin_base, uint32_t idx_bits,
+           uint32_t B, uint32_t* __restrict__ off, uint32_t* __restrict__ entries, uint32_t* __restrict__ keys, size_t ent_stride) {
+    extern __shared__ uint32_t sh_ent[];   // BIN_CAP packed entries
+    __shared__ uint32_t cnt[BIN_LO], start[BIN_LO], cur[BIN_LO];
+    const uint32_t h = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
+    const uint32_t m = min(bin_fill[(size_t)g * BIN_HI + h], BIN_CAP);
+    const uint32_t gbase = bin_base[(size_t)g * (BIN_HI + 1) + h];
+    const uint32_t* src = bins + ((size_t)g * BIN_HI + h) * BIN_CAP;
+    if (tid < BIN_LO) cnt[tid] = 0;
+    __syncthreads();
+    for (uint32_t k = tid; k < m; k += BIN_SORT_T) {
+        const uint32_t p = src[k];
+        sh_ent[k] = p;
+        atomicAdd(&cnt[p >> (idx_bits + 1)], 1u);
+    }
+    __syncthreads();
+    if (tid < BIN_LO) start[tid] = cnt[tid];
+    __syncthreads();
+    for (uint32_t d = 1; d < BIN_LO; d <<= 1) {   // inclusive scan of the 256 counts
+        uint32_t o = 0;
+        if (tid < BIN_LO && tid >= d) o = start[tid - d];
+        __syncthreads();
+        if (tid < BIN_LO) start[tid] += o;
+        __syncthreads();
+    }
+    if (tid < BIN_LO) {
+        const uint32_t excl = start[tid] - cnt[tid];
+        cur[tid] = excl;
+        off[(size_t)g * (B + 1) + h * BIN_LO + tid] = gbase + excl;
+    }
+    __syncthreads();
+    uint32_t* ent = entries + (size_t)g * ent_stride;
+    uint32_t* key = keys + (size_t)g * ent_stride;
+    const uint32_t idx_mask = (1u << idx_bits) - 1;
+    for (uint32_t k = tid; k < m; k += BIN_SORT_T) {
+        const uint32_t p = sh_ent[k], lo = p >> (idx_bits + 1);
+        const uint32_t pos = gbase + atomicAdd(&cur[lo], 1u);
+        ent[pos] = (p & idx_mask) | (((p >> idx_bits) & 1u) << 31);
+        key[pos] = h * BIN_LO + lo;
+    }
+}
+
 // ---- single-CTA exclusive scan per vector: offsets[g][0..B], cursor[g][b] = offsets[g][b]
 __global__ void __launch_bounds__(1024) k_scan(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint32_t B) {
     __shared__ uint32_t warp_tot[32];
@@ -577,18 +701,54 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     xyzz_t* l2 = (xyzz_t*)(base + o_l2);
     cudaStream_t st = ctx->stream;
 
-    B2R_CUDA(ctx, cudaMemsetAsync(cnt, 0, G * B * 4, st));
     B2R_CUDA(ctx, cudaMemsetAsync(bk, 0, G * B * sizeof(xyzz_t), st));
     dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
-    { KTimer kt(ctx, "msm_count", (double)G * n);
-    launch_digits<false>(c, !uniform, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cnt, nullptr, nullptr, 0); }
-    B2R_LAUNCH_CHECK(ctx);
-    { KTimer kt(ctx, "msm_scan");
-    k_scan<<<(unsigned)G, 1024, 0, st>>>(cnt, off, cur, B); }
-    B2R_LAUNCH_CHECK(ctx);
-    { KTimer kt(ctx, "msm_scatter", (double)G * n);
-    launch_digits<true>(c, !uniform, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cur, ent, key, ent_cap); }
-    B2R_LAUNCH_CHECK(ctx);
+    auto classic_sort = [&]() -> int32_t {
+        B2R_CUDA(ctx, cudaMemsetAsync(cnt, 0, G * B * 4, st));
+        { KTimer kt(ctx, "msm_count", (double)G * n);
+        launch_digits<false>(c, !uniform, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cnt, nullptr, nullptr, 0); }
+        B2R_LAUNCH_CHECK(ctx);
+        { KTimer kt(ctx, "msm_scan");
+        k_scan<<<(unsigned)G, 1024, 0, st>>>(cnt, off, cur, B); }
+        B2R_LAUNCH_CHECK(ctx);
+        { KTimer kt(ctx, "msm_scatter", (double)G * n);
+        launch_digits<true>(c, !uniform, gd, st, scalars_dev, (uint32_t)n, (uint32_t)bs->n, B, cur, ent, key, ent_cap); }
+        B2R_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    bool sorted = false;
+    uint32_t idx_bits = 0;
+    while (((size_t)1 << idx_bits) < (size_t)bs->n * W) idx_bits++;
+    static const char* bin_env = getenv("B2R_MSM_BINSORT");   // "0" disables, "1" forces (tests)
+    const bool want_bins = bin_env ? bin_env[0] == '1' : uniform;
+    if (want_bins && c == 16 && idx_bits + 9 <= 32 && B == BIN_HI * BIN_LO) {
+        uint32_t* bins = nullptr;
+        const size_t fill_bytes = (G * BIN_HI * 4 + 255) & ~(size_t)255, base_bytes = (G * (BIN_HI + 1) * 4 + 255) & ~(size_t)255;
+        B2R_TRY(scratch_get(ctx, SC_MSM_B, fill_bytes + base_bytes + 256 + G * (size_t)BIN_HI * BIN_CAP * 4 + G * 4, (void**)&bins));
+        uint32_t* bin_fill = bins;
+        uint32_t* bin_base = (uint32_t*)((char*)bins + fill_bytes);
+        uint32_t* bflags = (uint32_t*)((char*)bins + fill_bytes + base_bytes);
+        uint32_t* bin_data = (uint32_t*)((char*)bins + fill_bytes + base_bytes + 256 + ((G * 4 + 255) & ~(size_t)255));
+        B2R_CUDA(ctx, cudaMemsetAsync(bins, 0, fill_bytes + base_bytes + 256 + ((G * 4 + 255) & ~(size_t)255), st));
+        { KTimer kt(ctx, "msm_scatter", (double)G * n);
+        k_bin_scatter<16><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags);
+        B2R_LAUNCH_CHECK(ctx);
+        k_bin_prefix<<<(unsigned)G, BIN_HI, 0, st>>>(bin_fill, bin_base, off, B);
+        B2R_LAUNCH_CHECK(ctx);
+        static bool attr_set = false;
+        if (!attr_set) {
+            B2R_CUDA(ctx, cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BIN_CAP * 4)));
+            attr_set = true;
+        }
+        k_bin_sort<<<dim3(BIN_HI, (unsigned)G), BIN_SORT_T, BIN_CAP * 4, st>>>(bin_data, bin_fill, bin_base, idx_bits, B, off, ent, key, ent_cap);
+        B2R_LAUNCH_CHECK(ctx); }
+        std::vector<uint32_t> hf(G);
+        B2R_CUDA(ctx, cudaMemcpyAsync(hf.data(), bflags, G * 4, cudaMemcpyDeviceToHost, st));
+        B2R_CUDA(ctx, cudaStreamSynchronize(st));
+        sorted = true;
+        for (uint32_t f : hf) sorted = sorted && f == 0;   // a bin overflowed (the scalars were not uniform): general path
+    }
+    if (!sorted) B2R_TRY(classic_sort());
     double entries_total = (double)G * n;
     if (ctx->profile) {   // actual number of bucket entries of this group (the sum of the last offsets), for the roofline
         std::vector<uint32_t> last(G);
@@ -649,7 +809,7 @@ static size_t msm_group_bytes(const b2r_bases* bs, size_t n) {
     const uint32_t W = bs->W, B = 1u << (bs->c - 1);
     size_t ent_cap = n * W;
     size_t nch1 = (ent_cap + MSM_L1 - 1) / MSM_L1, slotsA = 2 * nch1, slotsB = 2 * ((slotsA + 15) / 16);
-    return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + ((size_t)B / 16 + (size_t)B / 64 + 8) * 128 + 4096 * 8;
+    return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + ((size_t)B / 16 + (size_t)B / 64 + 8) * 128 + 4096 * 8;   // (+ 10 MiB per vector in the second arena for the binned sort)
 }
 
 // `uniform`: the caller knows the non-zero scalars to be uniformly random field elements (no repeated values)
