@@ -298,8 +298,9 @@ __global__ void __launch_bounds__(256)
 k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_t idx_bits, uint32_t* __restrict__ bin_fill /*[G][128]*/,
               uint32_t* __restrict__ bins /*[G][128][CAP]*/, uint32_t* __restrict__ flags) {
     constexpr int W = (255 + C - 1) / C;
-    __shared__ uint32_t hist[BIN_HI], base[BIN_HI];
-    const uint32_t g = blockIdx.y, tid = threadIdx.x, i = blockIdx.x * 256 + tid;
+    __shared__ uint32_t hist[BIN_HI], base[BIN_HI], lstart[BIN_HI + 1];
+    __shared__ uint32_t stage[256 * W];   // the CTA's entries grouped by bin, so that every bin's run leaves as one coalesced store
+    const uint32_t g = blockIdx.y, tid = threadIdx.x, i = blockIdx.x * 256 + tid, lane = tid & 31, wid = tid >> 5;
     if (tid < BIN_HI) hist[tid] = 0;
     __syncthreads();
     fe_t s = Fr::zero();
@@ -309,15 +310,40 @@ k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, ui
     DigitLoopBins<C, 0, W>::run(s, carry, i, n_table, idx_bits, hist, packed, where);
     __syncthreads();
     if (tid < BIN_HI) base[tid] = hist[tid] ? atomicAdd(&bin_fill[(size_t)g * BIN_HI + tid], hist[tid]) : 0;
+    if (wid == 4) {   // exclusive scan of the 128 local counts by one warp, 4 bins per lane
+        const uint32_t c0 = hist[lane * 4], c1 = hist[lane * 4 + 1], c2 = hist[lane * 4 + 2], c3 = hist[lane * 4 + 3];
+        const uint32_t tot = c0 + c1 + c2 + c3;
+        uint32_t x = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= (uint32_t)d) x += y;
+        }
+        const uint32_t e = x - tot;
+        lstart[lane * 4] = e;
+        lstart[lane * 4 + 1] = e + c0;
+        lstart[lane * 4 + 2] = e + c0 + c1;
+        lstart[lane * 4 + 3] = e + c0 + c1 + c2;
+        if (lane == 31) lstart[BIN_HI] = x;
+    }
     __syncthreads();
-    uint32_t* mine = bins + (size_t)g * BIN_HI * BIN_CAP;
 #pragma unroll
     for (int j = 0; j < W; j++) {
         if (where[j] == 0xffffffffu) continue;
-        const uint32_t hi = where[j] >> 16, pos = base[hi] + (where[j] & 0xffffu);
-        if (pos < BIN_CAP) mine[(size_t)hi * BIN_CAP + pos] = packed[j];
-        else atomicOr(flags + g, 1u);
+        stage[lstart[where[j] >> 16] + (where[j] & 0xffffu)] = packed[j];
     }
+    __syncthreads();
+    uint32_t* mine = bins + (size_t)g * BIN_HI * BIN_CAP;
+    bool over = false;
+    for (uint32_t h = wid; h < BIN_HI; h += 8) {
+        const uint32_t b0 = lstart[h], cnt = lstart[h + 1] - b0, dst = base[h];
+        uint32_t* out = mine + (size_t)h * BIN_CAP;
+        for (uint32_t t = lane; t < cnt; t += 32) {
+            if (dst + t < BIN_CAP) out[dst + t] = stage[b0 + t];
+            else over = true;
+        }
+    }
+    if (over) atomicOr(flags + g, 1u);
 }
 
 // exclusive scan of the 128 bin sizes of every vector -> bin_base[g][0..128] (bin_base[g][128] = number of entries)
@@ -352,11 +378,7 @@ k_bin_sort(const uint32_t* __restrict__ bins, const uint32_t* __restrict__ bin_f
     const uint32_t* src = bins + ((size_t)g * BIN_HI + h) * BIN_CAP;
     if (tid < BIN_LO) cnt[tid] = 0;
     __syncthreads();
-    for (uint32_t k = tid; k < m; k += BIN_SORT_T) {
-        const uint32_t p = src[k];
-        sh_ent[k] = p;
-        atomicAdd(&cnt[p >> (idx_bits + 1)], 1u);
-    }
+    for (uint32_t k = tid; k < m; k += BIN_SORT_T) atomicAdd(&cnt[src[k] >> (idx_bits + 1)], 1u);
     __syncthreads();
     if (tid < BIN_LO) start[tid] = cnt[tid];
     __syncthreads();
@@ -373,14 +395,20 @@ k_bin_sort(const uint32_t* __restrict__ bins, const uint32_t* __restrict__ bin_f
         off[(size_t)g * (B + 1) + h * BIN_LO + tid] = gbase + excl;
     }
     __syncthreads();
-    uint32_t* ent = entries + (size_t)g * ent_stride;
-    uint32_t* key = keys + (size_t)g * ent_stride;
+    // second read of the bin (64-80 KB, L2-resident) places every entry at its sorted position in shared memory; the
+    // final list and keys then leave as fully coalesced stores
+    for (uint32_t k = tid; k < m; k += BIN_SORT_T) {
+        const uint32_t p = src[k];
+        sh_ent[atomicAdd(&cur[p >> (idx_bits + 1)], 1u)] = p;
+    }
+    __syncthreads();
+    uint32_t* ent = entries + (size_t)g * ent_stride + gbase;
+    uint32_t* key = keys + (size_t)g * ent_stride + gbase;
     const uint32_t idx_mask = (1u << idx_bits) - 1;
     for (uint32_t k = tid; k < m; k += BIN_SORT_T) {
-        const uint32_t p = sh_ent[k], lo = p >> (idx_bits + 1);
-        const uint32_t pos = gbase + atomicAdd(&cur[lo], 1u);
-        ent[pos] = (p & idx_mask) | (((p >> idx_bits) & 1u) << 31);
-        key[pos] = h * BIN_LO + lo;
+        const uint32_t p = sh_ent[k];
+        ent[k] = (p & idx_mask) | (((p >> idx_bits) & 1u) << 31);
+        key[k] = h * BIN_LO + (p >> (idx_bits + 1));
     }
 }
 
