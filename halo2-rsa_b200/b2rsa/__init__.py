@@ -292,7 +292,9 @@ class Context:
         self._ck(self.lib.b2r_rsa_program_build_var(self.h, bits_len, exp_limb_bits, k, C.byref(h)))
         return RsaProgram(self, h, bits_len, k)
 
-    BIGINT_OPS = {"refresh": 6, "add_mod": 7, "sub_mod": 8, "pow_mod": 9}
+    BIGINT_OPS = {"refresh": 6, "add_mod": 7, "sub_mod": 8, "pow_mod": 9, "is_zero": 10, "is_equal_fresh": 11, "is_less_than": 12,
+                  "is_less_than_or_equal": 13, "is_greater_than": 14, "is_greater_than_or_equal": 15, "is_in_field": 16,
+                  "square": 17, "square_mod": 18}
 
     def bigint_program(self, op: str, bits_len: int, k: int, exp_limb_bits: int = 5) -> "RsaProgram":
         """one BigIntInstructions method as the reference's unit-test circuits drive it; witness inputs (a, b, n | e)"""

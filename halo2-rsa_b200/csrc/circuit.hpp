@@ -1074,7 +1074,13 @@ inline AssignedValue record_rsa_pkcs1v15_var(RegionCtx& rc, unsigned bits_len, u
 // Single BigIntChip operations, as the reference's in-file test circuits drive them (src/big_integer/chip.rs:1470-2313).
 // Inputs (value nodes): a = 0..nl-1, b = nl..2nl-1, n = 2nl..3nl-1, e = 3nl.  Returns the cell whose value reports the
 // outcome (the last limb of the result); `out` receives the result limbs.
-enum BigIntTestOp : uint32_t { BT_REFRESH = 6, BT_ADD_MOD = 7, BT_SUB_MOD = 8, BT_POW_MOD = 9 };
+enum BigIntTestOp : uint32_t {
+    BT_REFRESH = 6, BT_ADD_MOD = 7, BT_SUB_MOD = 8, BT_POW_MOD = 9,
+    // the predicates (chip.rs:754-1006; test circuits chip.rs:2395-2795): the result integer is the one assigned bit
+    BT_IS_ZERO = 10, BT_IS_EQUAL_FRESH = 11, BT_IS_LESS_THAN = 12, BT_IS_LESS_THAN_OR_EQUAL = 13, BT_IS_GREATER_THAN = 14,
+    BT_IS_GREATER_THAN_OR_EQUAL = 15, BT_IS_IN_FIELD = 16,
+    BT_SQUARE = 17, BT_SQUARE_MOD = 18   // chip.rs:431-437, 642-649
+};
 inline AssignedValue record_bigint_op(RegionCtx& rc, uint32_t op, unsigned bits_len, unsigned exp_limb_bits, AssignedInteger* out) {
     const unsigned nl = bits_len / 64;
     configure_range_tags(rc, nl);
@@ -1099,6 +1105,27 @@ inline AssignedValue record_bigint_op(RegionCtx& rc, uint32_t op, unsigned bits_
         AssignedInteger e = chip.assign_integer(rc, e_u);
         AssignedInteger n = chip.assign_integer(rc, n_u);
         r = chip.pow_mod(rc, a, e, n, exp_limb_bits);
+    } else if (op >= BT_IS_ZERO && op <= BT_IS_IN_FIELD) {
+        AssignedInteger b = chip.assign_integer(rc, b_u);
+        AssignedValue bit;
+        switch (op) {
+            case BT_IS_ZERO: bit = chip.is_zero(rc, a); break;
+            case BT_IS_EQUAL_FRESH: bit = chip.is_equal_fresh(rc, a, b); break;
+            case BT_IS_LESS_THAN: bit = chip.is_less_than(rc, a, b); break;
+            case BT_IS_LESS_THAN_OR_EQUAL: bit = chip.is_less_than_or_equal(rc, a, b); break;
+            case BT_IS_GREATER_THAN: bit = chip.is_greater_than(rc, a, b); break;
+            case BT_IS_GREATER_THAN_OR_EQUAL: bit = chip.is_greater_than_or_equal(rc, a, b); break;
+            default: bit = chip.is_in_field(rc, a, b); break;
+        }
+        r.limbs.assign(1, bit);
+    } else if (op == BT_SQUARE || op == BT_SQUARE_MOD) {
+        AssignedInteger b = chip.assign_integer(rc, b_u);   // assigned and unused, to keep one input convention for every op
+        if (op == BT_SQUARE) {
+            r = chip.square(rc, a);
+        } else {
+            AssignedInteger n = chip.assign_integer(rc, n_u);
+            r = chip.square_mod(rc, a, n);
+        }
     } else {
         throw SynthError(-1, "record_bigint_op: unknown operation");
     }

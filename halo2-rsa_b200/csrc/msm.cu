@@ -848,7 +848,7 @@ int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev
         return 0;
     }
     size_t per_vec = msm_group_bytes(bs, n);
-    size_t budget = (size_t)12 << 30;  // work arena per group of vectors (fewer, larger launches: 180 GB of HBM)
+    size_t budget = (size_t)16 << 30;  // work arena per group of vectors (fewer, larger launches: 180 GB of HBM)
     size_t G = budget / per_vec;
     if (G < 1) G = 1;
     if (G > 1024) G = 1024;
@@ -860,11 +860,11 @@ int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev
 }
 
 // registration from device-resident affine points (d_in must not live in the SC_MSM_B arena)
-int32_t bases_register_dev(b2r_ctx* ctx, const affine_t* d_in, size_t n, b2r_bases** out) {
+int32_t bases_register_dev(b2r_ctx* ctx, const affine_t* d_in, size_t n, b2r_bases** out, uint32_t window) {
     *out = nullptr;
     b2r_bases* bs = new b2r_bases();
     bs->n = n;
-    bs->c = pick_window(n);
+    bs->c = (window == 10 || window == 13 || window == 16) ? window : pick_window(n);
     bs->W = (255 + bs->c - 1) / bs->c;
     cudaError_t e = cudaMalloc(&bs->table, (size_t)bs->W * n * sizeof(affine_t));
     if (e != cudaSuccess) {
@@ -893,6 +893,12 @@ void bases_destroy(b2r_bases* bs) {
     delete bs;
 }
 
+// the same points again with another window width (table row 0 is the points themselves): sparse scalar vectors
+// want few buckets (their bucket reduction costs more than their additions), dense ones few windows
+int32_t bases_register_rewindowed(b2r_ctx* ctx, const b2r_bases* src, uint32_t window, b2r_bases** out) {
+    return bases_register_dev(ctx, src->table, src->n, out, window);
+}
+
 // new base set S_j = sum_{i >= j} P_i of a registered set (see k_sfx_local)
 int32_t bases_register_suffix_sums(b2r_ctx* ctx, const b2r_bases* src, b2r_bases** out) {
     *out = nullptr;
@@ -910,7 +916,7 @@ int32_t bases_register_suffix_sums(b2r_ctx* ctx, const b2r_bases* src, b2r_bases
     k_sfx_write<<<gb, 128, 0, st>>>(src->table, tot, sx, n);
     k_normalize<<<(n + 127) / 128, 128, 0, st>>>(sx, sa, n);
     ctx->launches += 4;
-    int32_t rc = bases_register_dev(ctx, sa, n, out);  // synchronises the stream
+    int32_t rc = bases_register_dev(ctx, sa, n, out, 0);  // synchronises the stream
     cudaFree(buf);
     return rc;
 }
@@ -929,7 +935,7 @@ int32_t b2r_bases_register(b2r_ctx* ctx, const b2r_g1_affine* bases_host, size_t
     affine_t* d_in = nullptr;
     B2R_TRY(scratch_get(ctx, SC_STAGE, n * sizeof(affine_t), (void**)&d_in));
     B2R_CUDA(ctx, cudaMemcpyAsync(d_in, bases_host, n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
-    return bases_register_dev(ctx, d_in, n, out);
+    return bases_register_dev(ctx, d_in, n, out, 0);
 }
 
 int32_t b2r_bases_download(b2r_ctx* ctx, const b2r_bases* bases, b2r_g1_affine* out_host, size_t n) {

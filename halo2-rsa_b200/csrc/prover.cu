@@ -35,6 +35,7 @@ fe_t fr_zeta();
 fe_t fr_from_u64(uint64_t v);
 int32_t msm_batch_dev(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t m, size_t n, affine_t* out_dev, bool uniform);
 int32_t bases_register_suffix_sums(b2r_ctx* ctx, const b2r_bases* src, b2r_bases** out);
+int32_t bases_register_rewindowed(b2r_ctx* ctx, const b2r_bases* src, uint32_t window, b2r_bases** out);
 int32_t coset_ntt_grouped_dev(b2r_ctx* ctx, const fe_t* coeffs, size_t outer, uint64_t outer_stride, size_t inner, uint32_t k, uint32_t ext_k,
                               fe_t* out);
 void bases_destroy(b2r_bases* bs);
@@ -64,6 +65,12 @@ struct b2r_pk {
     const b2r_prog* prog = nullptr;
     const b2r_bases *g = nullptr, *gl = nullptr;
     b2r_bases* gl_sfx = nullptr;  // suffix sums of g_lagrange: commits the run-structured grand-product columns (msm.cu k_sfx_local)
+    // narrow-window copies for the sparse commitments, whose cost is the bucket reduction (2^15 buckets per vector at
+    // c = 16) rather than the additions: advice columns at c = 13, permuted lookup columns S' and the first differences
+    // of A' at c = 10
+    b2r_bases* gl_c13 = nullptr;
+    b2r_bases* gl_c10 = nullptr;
+    b2r_bases* gl_sfx_c10 = nullptr;
     uint32_t k = 0, ext_k = 0, n = 0, ext_n = 0, u = 0, T = 0;
     fe_t *fixed_values = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr;
     fe_t *sigma_values = nullptr, *sigma_polys = nullptr, *sigma_cosets = nullptr;
@@ -670,6 +677,9 @@ static void pk_release(b2r_pk* pk) {
     cudaFree(pk->sigma_values); cudaFree(pk->sigma_polys); cudaFree(pk->sigma_cosets);
     cudaFree(pk->l_cosets); cudaFree(pk->range_tags); cudaFree(pk->table);
     bases_destroy(pk->gl_sfx);
+    bases_destroy(pk->gl_c13);
+    bases_destroy(pk->gl_c10);
+    bases_destroy(pk->gl_sfx_c10);
     delete pk;
 }
 
@@ -784,6 +794,9 @@ int32_t b2r_rsa_keygen(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g, c
         KG_CUDA(cudaStreamSynchronize(st));  // lv goes out of scope
     }
     KG_TRY(bases_register_suffix_sums(ctx, g_lagrange, &pk->gl_sfx));
+    KG_TRY(bases_register_rewindowed(ctx, g_lagrange, 13, &pk->gl_c13));
+    KG_TRY(bases_register_rewindowed(ctx, g_lagrange, 10, &pk->gl_c10));
+    KG_TRY(bases_register_rewindowed(ctx, pk->gl_sfx, 10, &pk->gl_sfx_c10));
     // commitments of the verifying key
     {
         affine_t* d_cm = nullptr;
@@ -980,7 +993,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
 
     // ---- phase 1: witness + advice commitments
     B2R_TRY(witness_run(ctx, pk->prog, d_n, d_s, d_h, B, seed, (b2r_fr*)S.P, S.valid, p_base, /*p_stride=*/n, /*col_stride=*/(size_t)B * n));
-    B2R_TRY(msm_batch_dev(ctx, pk->gl, S.P + (size_t)SL_ADV * B * n, (size_t)NADV * B, n, S.cm, false));
+    B2R_TRY(msm_batch_dev(ctx, pk->gl_c13, S.P + (size_t)SL_ADV * B * n, (size_t)NADV * B, n, S.cm, false));
     B2R_CUDA(ctx, cudaMemcpyAsync(valid.data(), S.valid, B, cudaMemcpyDeviceToHost, st));
     B2R_TRY(fetch_points((size_t)NADV * B));
     parallel_for_proofs(B, [&](uint32_t p) {
@@ -1014,8 +1027,8 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
         }
         B2R_CUDA(ctx, cudaMemcpy2DAsync(SS, (size_t)B * n * 32, S.P + (size_t)(SL_LA + 1) * B * n, (size_t)2 * B * n * 32, (size_t)B * n * 32, NLOOK,
                                         cudaMemcpyDeviceToDevice, st));
-        B2R_TRY(msm_batch_dev(ctx, pk->gl_sfx, DA, (size_t)NLOOK * B, n, S.cm, false));
-        B2R_TRY(msm_batch_dev(ctx, pk->gl, SS, (size_t)NLOOK * B, n, S.cm + (size_t)NLOOK * B, false));
+        B2R_TRY(msm_batch_dev(ctx, pk->gl_sfx_c10, DA, (size_t)NLOOK * B, n, S.cm, false));
+        B2R_TRY(msm_batch_dev(ctx, pk->gl_c10, SS, (size_t)NLOOK * B, n, S.cm + (size_t)NLOOK * B, false));
     }
     B2R_CUDA(ctx, cudaMemcpyAsync(err.data(), S.err, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     B2R_TRY(fetch_points((size_t)2 * NLOOK * B));

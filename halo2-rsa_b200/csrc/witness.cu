@@ -680,7 +680,7 @@ int32_t b2r_rsa_program_build_var(b2r_ctx* ctx, uint32_t bits_len, uint32_t exp_
 int32_t b2r_bigint_program_build(b2r_ctx* ctx, uint32_t op, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out) {
     if (!ctx) return B2R_ERR_INVALID;
     if (!out) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: null argument");
-    if (op < BT_REFRESH || op > BT_POW_MOD) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: unknown operation");
+    if (op < BT_REFRESH || op > BT_SQUARE_MOD) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: unknown operation");
     if (exp_limb_bits == 0 || exp_limb_bits > 64) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: exp_limb_bits must be in [1, 64]");
     // inputs a | b | n | e: the third array carries n and e (num_limbs + 1 words per instance)
     return build_program(ctx, bits_len, k, bits_len / 64 + 1, [&](RegionCtx& rc) { return record_bigint_op(rc, op, bits_len, exp_limb_bits, nullptr); }, out);

@@ -149,7 +149,10 @@ int32_t b2r_rsa_program_build_var(b2r_ctx* ctx, uint32_t bits_len, uint32_t exp_
 /* One BigIntInstructions method as the reference's in-file unit-test circuits drive it (src/big_integer/chip.rs:
  * 1861-1899 refresh, 1948-1986 add_mod, 2027-2070 sub_mod, 2229-2271 pow_mod), for the methods the pkcs1v15 circuit
  * does not call.  op: 6 = mul + refresh (both operand orders, assert_equal_fresh), 7 = add_mod, 8 = sub_mod,
- * 9 = pow_mod with an assigned one-limb exponent.  Witness inputs: first array a, second array b, third array n
+ * 9 = pow_mod with an assigned one-limb exponent; the predicates of src/big_integer/chip.rs:754-1006 on (a, b), whose
+ * one result cell is also what is_valid reports: 10 = is_zero(a), 11 = is_equal_fresh, 12 = is_less_than,
+ * 13 = is_less_than_or_equal, 14 = is_greater_than, 15 = is_greater_than_or_equal, 16 = is_in_field(a, b);
+ * 17 = square(a) (:431-437), 18 = square_mod(a, n) (:642-649).  Witness inputs: first array a, second array b, third array n
  * followed by the exponent word (b2r_prog_aux_words = num_limbs + 1).  is_valid of the witness entry points is 0xFF
  * where the reference would have panicked and otherwise not meaningful for these programs (it tests the last result
  * limb against 1): compare the advice columns. */

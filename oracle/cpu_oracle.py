@@ -166,7 +166,9 @@ def rsa_synthesize(bits_len: int, k: int, n: int, sig: int, hashed: int, e: int 
 
 # ---- single BigIntChip operations (the reference's impl_bigint_test_circuit! bodies) ------------
 BIGINT_OPS = {"mul_kat": 0, "mul_mod": 1, "pow_mod_fixed_exp": 2, "add": 3, "sub": 4, "assert_in_field": 5,
-              "refresh": 6, "add_mod": 7, "sub_mod": 8, "pow_mod": 9}
+              "refresh": 6, "add_mod": 7, "sub_mod": 8, "pow_mod": 9, "is_zero": 10, "is_equal_fresh": 11, "is_less_than": 12,
+              "is_less_than_or_equal": 13, "is_greater_than": 14, "is_greater_than_or_equal": 15, "is_in_field": 16,
+              "square": 17, "square_mod": 18}
 
 
 def bigint_op(op: str, bits_len: int, k: int, a: int, b: int = 0, n: int = 0, exp_limb_bits: int = 5, with_advice: bool = False):

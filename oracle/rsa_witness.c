@@ -518,6 +518,25 @@ static void bi_assert_in_field(rctx* c, const bigchip* ch, const bint* a, const 
     mg_assert_one(c, &lt);
 }
 
+/* chip.rs:754-767 */
+static aval bi_is_zero(rctx* c, const bint* a) {
+    aval bit = mg_assign_bit(c, FR.one);
+    for (int i = 0; i < a->n; i++) { aval z = mg_is_zero(c, &a->l[i]); bit = mg_and(c, &bit, &z); }
+    return bit;
+}
+/* chip.rs:908-1006: the comparison family; `sub` reports its second output as 1 exactly when a <= b */
+static aval bi_is_lte(rctx* c, const bigchip* ch, const bint* a, const bint* b) {
+    bint tmp; aval is_overflowed; bi_sub(c, ch, a, b, &tmp, &is_overflowed); return is_overflowed;
+}
+static aval bi_is_lt(rctx* c, const bigchip* ch, const bint* a, const bint* b) {
+    aval lte = bi_is_lte(c, ch, a, b);
+    aval is_eq; bi_is_equal_fresh(c, a, b, &is_eq);
+    aval not_eq = mg_not(c, &is_eq);
+    return mg_and(c, &lte, &not_eq);
+}
+static aval bi_is_gt(rctx* c, const bigchip* ch, const bint* a, const bint* b) { aval lte = bi_is_lte(c, ch, a, b); return mg_not(c, &lte); }
+static aval bi_is_gte(rctx* c, const bigchip* ch, const bint* a, const bint* b) { aval lt = bi_is_lt(c, ch, a, b); return mg_not(c, &lt); }
+
 /* ---- MainGate::to_bits / compose (third-party maingate, restated from its published semantics) --------------
  * to_bits(composed, number_of_bits): every bit of the low number_of_bits bits of the value is assigned as a boolean
  * cell (assign_bit), least significant first; compose() lays the terms bit_i * 2^i out like decompose() does
@@ -841,7 +860,7 @@ int orc_bigint_op(orc_table* t, int op, int bits_len, const uint64_t* a_words, c
         bi_assign_integer(c, &ch, tmp, nl, &a);
         if (op == 9) { tmp[0] = fe_of_u64(b_words[0]); bi_assign_integer(c, &ch, tmp, 1, &b); }
         else if (op != 2) { for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(b_words[i]); bi_assign_integer(c, &ch, tmp, nl, &b); }
-        if (op == 1 || op == 2 || op == 5 || op >= 7) { for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(n_words[i]); bi_assign_integer(c, &ch, tmp, nl, &n); }
+        if (op == 1 || op == 2 || op == 5 || (op >= 7 && op <= 9) || op == 18) { for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(n_words[i]); bi_assign_integer(c, &ch, tmp, nl, &n); }
         if (op == 1) { bi_mul_mod(c, &ch, &a, &b, &n, &r); nout = r.n; }
         else if (op == 2) {
             uint8_t e_le[8]; for (int i = 0; i < 8; i++) e_le[i] = (uint8_t)(b_words[0] >> (8 * i));
@@ -858,6 +877,19 @@ int orc_bigint_op(orc_table* t, int op, int bits_len, const uint64_t* a_words, c
         else if (op == 7) { bi_add_mod(c, &ch, &a, &b, &n, &r); nout = r.n; }
         else if (op == 8) { bi_sub_mod(c, &ch, &a, &b, &n, &r); nout = r.n; }
         else if (op == 9) { bi_pow_mod(c, &ch, &a, &b, &n, n_words_len, &r); nout = r.n; }
+        else if (op >= 10 && op <= 16) {   /* the predicates: one result cell */
+            r.n = 1; nout = 1;
+            switch (op) {
+                case 10: r.l[0] = bi_is_zero(c, &a); break;
+                case 11: bi_is_equal_fresh(c, &a, &b, &r.l[0]); break;
+                case 12: case 16: r.l[0] = bi_is_lt(c, &ch, &a, &b); break;   /* is_in_field(a, n) = is_less_than(a, n) */
+                case 13: r.l[0] = bi_is_lte(c, &ch, &a, &b); break;
+                case 14: r.l[0] = bi_is_gt(c, &ch, &a, &b); break;
+                default: r.l[0] = bi_is_gte(c, &ch, &a, &b); break;
+            }
+        }
+        else if (op == 17) { bi_mul(c, &a, &a, &r); nout = r.n; }            /* square, chip.rs:430-437 */
+        else if (op == 18) { bi_mul_mod(c, &ch, &a, &a, &n, &r); nout = r.n; } /* square_mod, chip.rs:642-649 */
         else return -2;
     }
     for (int i = 0; i < nout; i++) fe_canon(&r.l[i].v, out + 4 * i);

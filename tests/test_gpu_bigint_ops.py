@@ -60,6 +60,37 @@ def test_bigint_op_advice_matches_oracle(ctx, op):
     prog.free()
 
 
+PREDICATES = {"is_zero": lambda a, b: a == 0, "is_equal_fresh": lambda a, b: a == b, "is_less_than": lambda a, b: a < b,
+              "is_less_than_or_equal": lambda a, b: a <= b, "is_greater_than": lambda a, b: a > b,
+              "is_greater_than_or_equal": lambda a, b: a >= b, "is_in_field": lambda a, b: a < b}
+
+
+@pytest.mark.parametrize("op", list(PREDICATES) + ["square", "square_mod"])
+def test_predicates_and_squares_match_oracle(ctx, op):
+    """the comparison family (chip.rs:754-1006) and square / square_mod (:431-437, :642-649): advice bit-exact against
+    the oracle, and the result cell (reported through is_valid for the predicates) against integer comparison"""
+    bits, k, batch = 512, 15, 6
+    nl = bits // 64
+    prog = ctx.bigint_program(op, bits, k)
+    r = random.Random(77)
+    n = r.getrandbits(bits) | (1 << (bits - 1)) | 1
+    a0 = r.getrandbits(bits) % n
+    pairs = [(a0, r.getrandbits(bits) % n), (a0, a0), (a0 >> 128, a0), (a0, a0 >> 128), (0, 0), (0, 1)]
+    a_l = np.stack([CO.int_to_limbs64(a, nl) for a, _ in pairs])
+    b_l = np.stack([CO.int_to_limbs64(b, nl) for _, b in pairs])
+    aux = np.stack([np.concatenate([CO.int_to_limbs64(n, nl), np.zeros(1, dtype=np.uint64)]) for _ in pairs])
+    adv, valid = prog.witness_batch(a_l, b_l, aux)
+    for i, (a, b) in enumerate(pairs):
+        limbs, bad, want = CO.bigint_op(op, bits, k, a, b, n, with_advice=True)
+        assert limbs is not None and bad == 0
+        assert np.array_equal(adv[i], want), f"{op}: instance {i}"
+        if op in PREDICATES:
+            assert limbs == [int(PREDICATES[op](a, b))] and int(valid[i]) == limbs[0]
+        elif op == "square_mod":
+            assert sum(l << (64 * j) for j, l in enumerate(limbs)) == a * a % n
+    prog.free()
+
+
 def test_rsa_var_witness_and_proof(ctx):
     """RSAPubE::Var end to end at RSA-512 / k = 17 (17 exponent bits -> 34 mul_mod): advice equal to the oracle, a wrong
     exponent gives is_valid = 0, and a full proof over the Var circuit's own keygen verifies with the oracle verifier"""

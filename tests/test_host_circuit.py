@@ -92,7 +92,9 @@ def _assert_same_layout(d, dig):
     assert int(d["range"]) == hr
 
 
-@pytest.mark.parametrize("op,opid", [("refresh", 6), ("add_mod", 7), ("sub_mod", 8), ("pow_mod", 9)])
+@pytest.mark.parametrize("op,opid", [("refresh", 6), ("add_mod", 7), ("sub_mod", 8), ("pow_mod", 9)] + [(o, CO.BIGINT_OPS[o]) for o in (
+    "is_zero", "is_equal_fresh", "is_less_than", "is_less_than_or_equal", "is_greater_than", "is_greater_than_or_equal", "is_in_field",
+    "square", "square_mod")])
 def test_bigint_ops_layout_equals_oracle_layout(exe, op, opid):
     """the BigIntInstructions methods the pkcs1v15 circuit does not call (refresh, add_mod, sub_mod, variable-exponent
     pow_mod: src/big_integer/chip.rs:168-233, 452-529, 664-696) recorded by the host mirror vs the oracle's row-by-row

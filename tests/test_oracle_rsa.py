@@ -179,6 +179,37 @@ def test_pow_mod_variable_exponent():
     assert bad > 0
 
 
+def test_predicates_match_integer_comparisons():
+    """chip.rs:2395-2795 (test_is_zero ... test_bad_in_field): the seven predicates against Python integer comparison,
+    on the reference's own shapes - a >> 128 < b, a <= a, a > a >> 128, a >= a, a in field n - and their negations"""
+    bits, k = 512, 15
+    a, b = _rand(bits, 31) | (1 << (bits - 1)), _rand(bits, 32) | (1 << (bits - 2))
+    small = a >> 128
+    truth = {"is_equal_fresh": lambda x, y: x == y, "is_less_than": lambda x, y: x < y, "is_less_than_or_equal": lambda x, y: x <= y,
+             "is_greater_than": lambda x, y: x > y, "is_greater_than_or_equal": lambda x, y: x >= y, "is_in_field": lambda x, y: x < y}
+    pairs = [(small, b), (b, small), (a, a), (a, a - 1), (a - 1, a), (0, 0), (0, 1), (a, a ^ (1 << 300)), ((1 << bits) - 1, (1 << bits) - 1)]
+    for op, f in truth.items():
+        for x, y in pairs:
+            limbs, bad = CO.bigint_op(op, bits, k, x, y)
+            assert bad == 0 and limbs == [int(f(x, y))], (op, x, y)
+    for x in (0, 1, a, 1 << 448):
+        limbs, bad = CO.bigint_op("is_zero", bits, k, x, 0)
+        assert bad == 0 and limbs == [int(x == 0)]
+
+
+def test_square_and_square_mod():
+    """chip.rs:431-437 / 642-649: square = mul(a, a) (unreduced limbs), square_mod = mul_mod(a, a, n)"""
+    bits, k = 512, 15
+    nl = bits // 64
+    n = _rand(bits, 41) | (1 << (bits - 1)) | 1
+    a = _rand(bits, 42) % n
+    limbs, bad = CO.bigint_op("square", bits, k, a, 0)
+    al = [(a >> (64 * i)) & ((1 << 64) - 1) for i in range(nl)]
+    assert bad == 0 and limbs == [sum(al[j] * al[i - j] for j in range(nl) if 0 <= i - j < nl) for i in range(2 * nl - 1)]
+    limbs, bad = CO.bigint_op("square_mod", bits, k, a, 0, n)
+    assert bad == 0 and sum(l << (64 * i) for i, l in enumerate(limbs)) == a * a % n
+
+
 def test_rsa_variable_exponent_circuit():
     """src/chip.rs:372-400 shape (RSAPubE::Var): the pkcs1v15 circuit with e = 65537 given as a witness, 17 exponent bits"""
     bits, k = 512, 17
