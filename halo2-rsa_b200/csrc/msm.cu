@@ -260,71 +260,73 @@ static void launch_digits(uint32_t c, bool agg, dim3 grid, cudaStream_t st, cons
 #undef B2R_DIG
 }
 
-// digit loop of k_bin_scatter: window J of the scalar -> packed entry (table index | sign << idx_bits | low 8 bucket bits
-// << (idx_bits + 1)) and its rank among the CTA's entries of the same high-7-bit bin
-template <int C, int J, int W>
+// digit loop of k_bin_scatter: window J of the scalar -> packed entry (table index | sign << idx_bits | low LB bucket bits
+// << (idx_bits + 1)) and its rank among the CTA's entries of the same high-bits bin
+template <int C, int J, int W, int LB>
 struct DigitLoopBins {
     static __device__ __forceinline__ void run(const fe_t& k, uint32_t& carry, uint32_t i, uint32_t n_table, uint32_t idx_bits, uint32_t* hist,
                                                uint32_t* packed, uint32_t* where) {
         const int32_t d = signed_digit<C, J>(k, carry);
         if (d != 0) {
-            const uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1, hi = b >> 8, lo = b & 255u;
+            const uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1, hi = b >> LB, lo = b & ((1u << LB) - 1);
             packed[J] = ((uint32_t)J * n_table + i) | ((d < 0 ? 1u : 0u) << idx_bits) | (lo << (idx_bits + 1));
             where[J] = (hi << 16) | atomicAdd(&hist[hi], 1u);
         } else {
             packed[J] = 0;
             where[J] = 0xffffffffu;
         }
-        DigitLoopBins<C, J + 1, W>::run(k, carry, i, n_table, idx_bits, hist, packed, where);
+        DigitLoopBins<C, J + 1, W, LB>::run(k, carry, i, n_table, idx_bits, hist, packed, where);
     }
 };
-template <int C, int W>
-struct DigitLoopBins<C, W, W> {
+template <int C, int W, int LB>
+struct DigitLoopBins<C, W, W, LB> {
     static __device__ __forceinline__ void run(const fe_t&, uint32_t&, uint32_t, uint32_t, uint32_t, uint32_t*, uint32_t*, uint32_t*) {}
 };
 
 // ---- binned counting sort for vectors the caller declares uniform (c = 16) ---------------------------------------
 // The per-entry global atomics and scattered 4-byte stores of k_digits are what bound it on dense random scalars
 // (56 us per 2^17 vector against 350 us of accumulation).  Uniform digits make every group of 256 buckets receive
-// ~16 K entries, so the sort is done in two coalesced steps: k_bin_scatter partitions the entries by the high 7 bits of
-// the bucket (shared-memory ranks, one global reservation per CTA and bin, runs of ~32 entries written together into
+// ~16 K entries, so the sort is done in two coalesced steps: k_bin_scatter partitions the entries by the high 7 (or 8) bits
+// of the bucket (shared-memory ranks, one global reservation per CTA and bin, runs of ~32 entries written together into
 // fixed-capacity bins), k_bin_sort finishes each bin in shared memory by the low 8 bits and writes the final sorted
 // list, the keys and the bucket offsets.  A bin that overflows its capacity raises a flag and the group is redone by
 // the general kernels.
-static constexpr uint32_t BIN_HI = 128, BIN_LO = 256, BIN_CAP = 20480, BIN_SORT_T = 512;
+// HB = high bits: 7 (128 bins of 256 buckets) up to 2^17 scalars, 8 (256 bins of 128 buckets) for 2^18, so that a bin
+// holds ~16 K entries either way.
+static constexpr uint32_t BIN_CAP = 20480, BIN_SORT_T = 512, BIN_MAX = 256;
 
-template <int C>
+template <int C, int HB>
 __global__ void __launch_bounds__(256)
-k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_t idx_bits, uint32_t* __restrict__ bin_fill /*[G][128]*/,
-              uint32_t* __restrict__ bins /*[G][128][CAP]*/, uint32_t* __restrict__ flags) {
+k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_t idx_bits, uint32_t* __restrict__ bin_fill /*[G][HI]*/,
+              uint32_t* __restrict__ bins /*[G][HI][CAP]*/, uint32_t* __restrict__ flags) {
     constexpr int W = (255 + C - 1) / C;
-    __shared__ uint32_t hist[BIN_HI], base[BIN_HI], lstart[BIN_HI + 1];
+    constexpr uint32_t HI = 1u << HB, PER = HI / 32;
+    __shared__ uint32_t hist[HI], base[HI], lstart[HI + 1];
     __shared__ uint32_t stage[256 * W];   // the CTA's entries grouped by bin, so that every bin's run leaves as one coalesced store
     const uint32_t g = blockIdx.y, tid = threadIdx.x, i = blockIdx.x * 256 + tid, lane = tid & 31, wid = tid >> 5;
-    if (tid < BIN_HI) hist[tid] = 0;
+    if (tid < HI) hist[tid] = 0;
     __syncthreads();
     fe_t s = Fr::zero();
     if (i < n) s = Fr::from_mont(ldg_fe(scalars + (size_t)g * n + i));
     uint32_t packed[W], where[W];   // where = hi << 16 | rank inside the CTA's share of the bin; 0xffffffff = no entry
     uint32_t carry = 0;
-    DigitLoopBins<C, 0, W>::run(s, carry, i, n_table, idx_bits, hist, packed, where);
+    DigitLoopBins<C, 0, W, C - 1 - HB>::run(s, carry, i, n_table, idx_bits, hist, packed, where);
     __syncthreads();
-    if (tid < BIN_HI) base[tid] = hist[tid] ? atomicAdd(&bin_fill[(size_t)g * BIN_HI + tid], hist[tid]) : 0;
-    if (wid == 4) {   // exclusive scan of the 128 local counts by one warp, 4 bins per lane
-        const uint32_t c0 = hist[lane * 4], c1 = hist[lane * 4 + 1], c2 = hist[lane * 4 + 2], c3 = hist[lane * 4 + 3];
-        const uint32_t tot = c0 + c1 + c2 + c3;
+    if (tid < HI) base[tid] = hist[tid] ? atomicAdd(&bin_fill[(size_t)g * HI + tid], hist[tid]) : 0;
+    if (wid == 7) {   // exclusive scan of the local counts by one warp, PER bins per lane
+        uint32_t cn[PER], tot = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < PER; q++) { cn[q] = hist[lane * PER + q]; tot += cn[q]; }
         uint32_t x = tot;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
             if (lane >= (uint32_t)d) x += y;
         }
-        const uint32_t e = x - tot;
-        lstart[lane * 4] = e;
-        lstart[lane * 4 + 1] = e + c0;
-        lstart[lane * 4 + 2] = e + c0 + c1;
-        lstart[lane * 4 + 3] = e + c0 + c1 + c2;
-        if (lane == 31) lstart[BIN_HI] = x;
+        uint32_t e = x - tot;
+#pragma unroll
+        for (uint32_t q = 0; q < PER; q++) { lstart[lane * PER + q] = e; e += cn[q]; }
+        if (lane == 31) lstart[HI] = x;
     }
     __syncthreads();
 #pragma unroll
@@ -333,9 +335,9 @@ k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, ui
         stage[lstart[where[j] >> 16] + (where[j] & 0xffffu)] = packed[j];
     }
     __syncthreads();
-    uint32_t* mine = bins + (size_t)g * BIN_HI * BIN_CAP;
+    uint32_t* mine = bins + (size_t)g * HI * BIN_CAP;
     bool over = false;
-    for (uint32_t h = wid; h < BIN_HI; h += 8) {
+    for (uint32_t h = wid; h < HI; h += 8) {
         const uint32_t b0 = lstart[h], cnt = lstart[h + 1] - b0, dst = base[h];
         uint32_t* out = mine + (size_t)h * BIN_CAP;
         for (uint32_t t = lane; t < cnt; t += 32) {
@@ -346,53 +348,53 @@ k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, ui
     if (over) atomicOr(flags + g, 1u);
 }
 
-// exclusive scan of the 128 bin sizes of every vector -> bin_base[g][0..128] (bin_base[g][128] = number of entries)
-__global__ void __launch_bounds__(BIN_HI) k_bin_prefix(const uint32_t* __restrict__ bin_fill, uint32_t* __restrict__ bin_base, uint32_t* __restrict__ off,
-                                                       uint32_t B) {
-    __shared__ uint32_t sh[BIN_HI];
+// exclusive scan of the HI bin sizes of every vector -> bin_base[g][0..HI] (bin_base[g][HI] = number of entries)
+__global__ void __launch_bounds__(BIN_MAX) k_bin_prefix(const uint32_t* __restrict__ bin_fill, uint32_t* __restrict__ bin_base, uint32_t* __restrict__ off,
+                                                        uint32_t B, uint32_t HI) {
+    __shared__ uint32_t sh[BIN_MAX];
     const uint32_t g = blockIdx.x, t = threadIdx.x;
-    const uint32_t v = min(bin_fill[(size_t)g * BIN_HI + t], BIN_CAP);
+    const uint32_t v = t < HI ? min(bin_fill[(size_t)g * HI + t], BIN_CAP) : 0;
     sh[t] = v;
     __syncthreads();
-    for (uint32_t d = 1; d < BIN_HI; d <<= 1) {
+    for (uint32_t d = 1; d < BIN_MAX; d <<= 1) {
         const uint32_t o = t >= d ? sh[t - d] : 0;
         __syncthreads();
         sh[t] += o;
         __syncthreads();
     }
-    bin_base[(size_t)g * (BIN_HI + 1) + t] = sh[t] - v;
-    if (t == BIN_HI - 1) {
-        bin_base[(size_t)g * (BIN_HI + 1) + BIN_HI] = sh[t];
+    if (t < HI) bin_base[(size_t)g * (HI + 1) + t] = sh[t] - v;
+    if (t == HI - 1) {
+        bin_base[(size_t)g * (HI + 1) + HI] = sh[t];
         off[(size_t)g * (B + 1) + B] = sh[t];
     }
 }
 
 __global__ void __launch_bounds__(BIN_SORT_T)
 k_bin_sort(const uint32_t* __restrict__ bins, const uint32_t* __restrict__ bin_fill, const uint32_t* __restrict__ bin_base, uint32_t idx_bits,
-           uint32_t B, uint32_t* __restrict__ off, uint32_t* __restrict__ entries, uint32_t* __restrict__ keys, size_t ent_stride) {
+           uint32_t B, uint32_t HI, uint32_t* __restrict__ off, uint32_t* __restrict__ entries, uint32_t* __restrict__ keys, size_t ent_stride) {
     extern __shared__ uint32_t sh_ent[];   // BIN_CAP packed entries
-    __shared__ uint32_t cnt[BIN_LO], start[BIN_LO], cur[BIN_LO];
-    const uint32_t h = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
-    const uint32_t m = min(bin_fill[(size_t)g * BIN_HI + h], BIN_CAP);
-    const uint32_t gbase = bin_base[(size_t)g * (BIN_HI + 1) + h];
-    const uint32_t* src = bins + ((size_t)g * BIN_HI + h) * BIN_CAP;
-    if (tid < BIN_LO) cnt[tid] = 0;
+    __shared__ uint32_t cnt[BIN_MAX], start[BIN_MAX], cur[BIN_MAX];
+    const uint32_t h = blockIdx.x, g = blockIdx.y, tid = threadIdx.x, LO = B / HI;
+    const uint32_t m = min(bin_fill[(size_t)g * HI + h], BIN_CAP);
+    const uint32_t gbase = bin_base[(size_t)g * (HI + 1) + h];
+    const uint32_t* src = bins + ((size_t)g * HI + h) * BIN_CAP;
+    if (tid < BIN_MAX) cnt[tid] = 0;
     __syncthreads();
     for (uint32_t k = tid; k < m; k += BIN_SORT_T) atomicAdd(&cnt[src[k] >> (idx_bits + 1)], 1u);
     __syncthreads();
-    if (tid < BIN_LO) start[tid] = cnt[tid];
+    if (tid < BIN_MAX) start[tid] = cnt[tid];
     __syncthreads();
-    for (uint32_t d = 1; d < BIN_LO; d <<= 1) {   // inclusive scan of the 256 counts
+    for (uint32_t d = 1; d < BIN_MAX; d <<= 1) {   // inclusive scan of the counts
         uint32_t o = 0;
-        if (tid < BIN_LO && tid >= d) o = start[tid - d];
+        if (tid < BIN_MAX && tid >= d) o = start[tid - d];
         __syncthreads();
-        if (tid < BIN_LO) start[tid] += o;
+        if (tid < BIN_MAX) start[tid] += o;
         __syncthreads();
     }
-    if (tid < BIN_LO) {
+    if (tid < BIN_MAX) {
         const uint32_t excl = start[tid] - cnt[tid];
         cur[tid] = excl;
-        off[(size_t)g * (B + 1) + h * BIN_LO + tid] = gbase + excl;
+        if (tid < LO) off[(size_t)g * (B + 1) + h * LO + tid] = gbase + excl;
     }
     __syncthreads();
     // second read of the bin (64-80 KB, L2-resident) places every entry at its sorted position in shared memory; the
@@ -408,7 +410,7 @@ k_bin_sort(const uint32_t* __restrict__ bins, const uint32_t* __restrict__ bin_f
     for (uint32_t k = tid; k < m; k += BIN_SORT_T) {
         const uint32_t p = sh_ent[k];
         ent[k] = (p & idx_mask) | (((p >> idx_bits) & 1u) << 31);
-        key[k] = h * BIN_LO + (p >> (idx_bits + 1));
+        key[k] = h * LO + (p >> (idx_bits + 1));
     }
 }
 
@@ -747,28 +749,31 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     bool sorted = false;
     uint32_t idx_bits = 0;
     while (((size_t)1 << idx_bits) < (size_t)bs->n * W) idx_bits++;
-    static const char* bin_env = getenv("B2R_MSM_BINSORT");   // "0" disables, "1" forces (tests)
+    const char* bin_env = getenv("B2R_MSM_BINSORT");   // "0" disables, "1" forces (tests); read per call so a test can toggle it
     const bool want_bins = bin_env ? bin_env[0] == '1' : uniform;
-    if (want_bins && c == 16 && idx_bits + 9 <= 32 && B == BIN_HI * BIN_LO) {
+    // bins of ~n * W / HI entries: 128 bins up to 2^17 scalars, 256 bins up to 2^18 (capacity 20480 per bin, 25 % slack)
+    const uint32_t HI = (size_t)n * W * 9 / 8 <= (size_t)128 * BIN_CAP ? 128u : 256u;
+    if (want_bins && c == 16 && idx_bits + 9 <= 32 && (size_t)n * W * 9 / 8 <= (size_t)HI * BIN_CAP) {
         uint32_t* bins = nullptr;
-        const size_t fill_bytes = (G * BIN_HI * 4 + 255) & ~(size_t)255, base_bytes = (G * (BIN_HI + 1) * 4 + 255) & ~(size_t)255;
-        B2R_TRY(scratch_get(ctx, SC_MSM_B, fill_bytes + base_bytes + 256 + G * (size_t)BIN_HI * BIN_CAP * 4 + G * 4, (void**)&bins));
+        const size_t fill_bytes = (G * HI * 4 + 255) & ~(size_t)255, base_bytes = (G * (HI + 1) * 4 + 255) & ~(size_t)255;
+        B2R_TRY(scratch_get(ctx, SC_MSM_B, fill_bytes + base_bytes + 256 + G * (size_t)HI * BIN_CAP * 4 + G * 4, (void**)&bins));
         uint32_t* bin_fill = bins;
         uint32_t* bin_base = (uint32_t*)((char*)bins + fill_bytes);
         uint32_t* bflags = (uint32_t*)((char*)bins + fill_bytes + base_bytes);
         uint32_t* bin_data = (uint32_t*)((char*)bins + fill_bytes + base_bytes + 256 + ((G * 4 + 255) & ~(size_t)255));
         B2R_CUDA(ctx, cudaMemsetAsync(bins, 0, fill_bytes + base_bytes + 256 + ((G * 4 + 255) & ~(size_t)255), st));
         { KTimer kt(ctx, "msm_scatter", (double)G * n);
-        k_bin_scatter<16><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags);
+        if (HI == 128) k_bin_scatter<16, 7><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags);
+        else k_bin_scatter<16, 8><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags);
         B2R_LAUNCH_CHECK(ctx);
-        k_bin_prefix<<<(unsigned)G, BIN_HI, 0, st>>>(bin_fill, bin_base, off, B);
+        k_bin_prefix<<<(unsigned)G, BIN_MAX, 0, st>>>(bin_fill, bin_base, off, B, HI);
         B2R_LAUNCH_CHECK(ctx);
         static bool attr_set = false;
         if (!attr_set) {
             B2R_CUDA(ctx, cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BIN_CAP * 4)));
             attr_set = true;
         }
-        k_bin_sort<<<dim3(BIN_HI, (unsigned)G), BIN_SORT_T, BIN_CAP * 4, st>>>(bin_data, bin_fill, bin_base, idx_bits, B, off, ent, key, ent_cap);
+        k_bin_sort<<<dim3(HI, (unsigned)G), BIN_SORT_T, BIN_CAP * 4, st>>>(bin_data, bin_fill, bin_base, idx_bits, B, HI, off, ent, key, ent_cap);
         B2R_LAUNCH_CHECK(ctx); }
         std::vector<uint32_t> hf(G);
         B2R_CUDA(ctx, cudaMemcpyAsync(hf.data(), bflags, G * 4, cudaMemcpyDeviceToHost, st));
@@ -837,7 +842,7 @@ static size_t msm_group_bytes(const b2r_bases* bs, size_t n) {
     const uint32_t W = bs->W, B = 1u << (bs->c - 1);
     size_t ent_cap = n * W;
     size_t nch1 = (ent_cap + MSM_L1 - 1) / MSM_L1, slotsA = 2 * nch1, slotsB = 2 * ((slotsA + 15) / 16);
-    return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + ((size_t)B / 16 + (size_t)B / 64 + 8) * 128 + 4096 * 8;   // (+ 10 MiB per vector in the second arena for the binned sort)
+    return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + ((size_t)B / 16 + (size_t)B / 64 + 8) * 128 + 4096 * 8;   // (+ 10 - 20 MiB per vector in the second arena for the binned sort)
 }
 
 // `uniform`: the caller knows the non-zero scalars to be uniformly random field elements (no repeated values)

@@ -89,3 +89,21 @@ def test_msm_2p16_closed_form(ctx):
     want = O.g1_mul(O.G1_GEN, sum(s * (i + 1) for i, s in enumerate(sc)) % O.R_MOD)
     assert got == want
     bs.free()
+
+
+@pytest.mark.parametrize("log_n", [17, 18])
+def test_msm_binned_sort_path(ctx, log_n, monkeypatch):
+    """the two-pass binned counting sort (msm.cu k_bin_scatter / k_bin_sort: 128 bins up to 2^17 scalars, 256 bins at
+    2^18) forced through the generic entry point: uniform vectors against the closed form, and a vector of one repeated
+    scalar, which overflows a bin and must come back through the general kernels with the same answer"""
+    monkeypatch.setenv("B2R_MSM_BINSORT", "1")
+    n = 1 << log_n
+    pts = O.g1_multiples(n)
+    bs = ctx.bases_register(g1_to_np(pts))
+    tri = n * (n + 1) // 2
+    vecs = [O.fr_stream(0xB1 + log_n, n), O.fr_stream(0xB2 + log_n, n), [0x1234567 * 0x10001] * n]
+    got = np_to_g1(ctx.msm_batch(bs, np.stack([fr_to_np(v) for v in vecs])))
+    for j, v in enumerate(vecs):
+        k = (v[0] * tri if j == 2 else sum(s * (i + 1) for i, s in enumerate(v))) % O.R_MOD
+        assert got[j] == O.g1_mul(O.G1_GEN, k), f"vector {j}"
+    bs.free()
