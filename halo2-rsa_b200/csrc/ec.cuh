@@ -175,7 +175,9 @@ B2R_HD void xyzz_madd_ls(xyzz_t& acc, const affine_t& q, bool neg) {
     fe_t PP = Fq::sqr(P);
     fe_t PPP = Fq::mul(P, PP);
     fe_t Q = Fq::mul(acc.x, PP);
-    fe_t X3 = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
+    // R^2 through the general product: seven values are live here, and the dedicated squaring's extra accumulator
+    // words push k_accum_entries (127 registers at 4 CTAs/SM) into spills - measured slower than it saves
+    fe_t X3 = Fq::sub(Fq::sub(Fq::mul(R, R), PPP), Fq::dbl(Q));
     fe_t Y3 = Fq::sub(Fq::mul(R, Fq::sub(Q, X3)), Fq::mul(acc.y, PPP));
     fe_t ZZ3 = Fq::mul(acc.zz, PP);
     fe_t ZZZ3 = Fq::mul(acc.zzz, PPP);

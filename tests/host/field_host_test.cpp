@@ -39,6 +39,7 @@ static void run(const char* name, int n) {
         printf("%s ", name);
         pr(a); pr(b); pr(F::mul(a, b)); pr(F::add(a, b)); pr(F::sub(a, b)); pr(F::neg(a));
         if (it < 8) pr(F::inv(a)); else pr(F::zero());
+        pr(F::sqr(a));
         printf("\n");
     }
 }

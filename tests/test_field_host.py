@@ -21,9 +21,10 @@ def test_field_cuh_host_build_matches_python():
     for line in out.splitlines():
         f = line.split()
         mod = O.R_MOD if f[0] == "fr" else O.Q_MOD
-        a, b, mul, add, sub, neg, inv = (int(x, 16) for x in f[1:8])
+        a, b, mul, add, sub, neg, inv, sqr = (int(x, 16) for x in f[1:9])
         rinv = pow(R, -1, mod)
         assert mul == a * b * rinv % mod
+        assert sqr == a * a * rinv % mod      # the dedicated squaring (36 + 64 wide products)
         assert add == (a + b) % mod and sub == (a - b) % mod and neg == (-a) % mod
         if inv:
             # Montgomery inverse: inv(aR) = a^-1 R  =>  a_m * inv_m = R^2 (mod p)
