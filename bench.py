@@ -45,7 +45,7 @@ FULL_MSM_PER_PROOF, MSM_WINDOWS = 16, 16  # grand products 7, random poly 1, h p
 # profiles/r01_ncu_final.md: the launch over the 256 quotient-piece columns (full-size scalars) moved 44.52 GB + 2.32 GB
 ACCUM_TRAFFIC_BYTES = 46.8e9
 ACCUM_TRAFFIC_VECTORS = 256
-ACCUM_TRAFFIC_SOURCE = ("ncu --set full, one k_accum_entries launch over 256 x 2^17 full-size scalars: 44.52 GB read + 2.32 GB written "
+ACCUM_TRAFFIC_SOURCE = ("ncu --set full, one k_accum_entries launch over 256 x 2^17 full-size scalars: 44.55 GB read + 2.32 GB written "
                         "(algorithmic 3.22 GB; the rest is the 16 x 64 B table gathers per scalar of the resident-table design, "
                         "37 % L2 hits) - profiles/r01_ncu_final.md")
 
@@ -318,15 +318,16 @@ def main():
                     "avg_launch_ms": kms / kcnt, "share_of_step": kms / ms,
                     "note": "integer-multiplier bound (254-bit field products), not HBM bound: see int_pipe and DESIGN.md section 4"}
             # the roofline that binds this kernel (profiles/r01_pipebench.md): IMAD.WIDE issues at 32 lanes/clk/SM on B200, a
-            # Montgomery product is 128 of them, a mixed addition 10 products -> 148 SMs * 32 / 1280 additions per clock
+            # Montgomery product is 128 of them, the dedicated squaring 100, a mixed addition 9 products + 1 squaring
+            # -> 148 SMs * 32 / 1252 additions per clock
             sm_clk = 1.965e9
-            ceiling = 148 * 32 / 1280.0 * sm_clk / 1e9
+            ceiling = 148 * 32 / 1252.0 * sm_clk / 1e9
             roof["int_pipe"] = {"unit": "G mixed additions/s", "achieved": accum_entries / (kms / 1e3) / 1e9, "peak": ceiling,
                                 "frac": accum_entries / (kms / 1e3) / 1e9 / ceiling,
                                 "additions_per_step": accum_entries / args.steps,
                                 "how": "bucket entries counted by the library (zero digits and, for the grand-product columns, rows where the "
                                        "column does not change are skipped) / kernel time; peak = 148 SMs x 32 IMAD.WIDE lanes/clk / "
-                                       "(10 products x 128 IMAD.WIDE) at 1965 MHz"}
+                                       "(9 products x 128 + 1 squaring x 100 IMAD.WIDE) at 1965 MHz"}
             roof["traffic"] = ACCUM_TRAFFIC_BYTES
             roof["traffic_algorithmic_bytes_of_that_launch"] = ACCUM_TRAFFIC_VECTORS * n * MSM_BYTES_PER_TERM
             roof["traffic_source"] = ACCUM_TRAFFIC_SOURCE
