@@ -431,7 +431,10 @@ static_assert(NSETS == 2, "constraint numbering below assumes two permutation se
 // h = sum_k C_k y^(NCONS-1-k) / (X^n - 1).  halo2 folds the constraints by Horner in y (two products per constraint);
 // every C_k here is l(X) * e_k with l one of {1, l0, l_last, l_active}, so the sum is regrouped as
 // gate y^30 + l0 sum(e_k y^..) + l_last sum(..) + l_active sum(..): one product per constraint plus three.
-__global__ void __launch_bounds__(128, 3) k_quotient(const QuotArgs A, const DevConsts C) {
+#ifndef B2R_QMINB
+#define B2R_QMINB 3
+#endif
+__global__ void __launch_bounds__(128, B2R_QMINB) k_quotient(const QuotArgs A, const DevConsts C) {
     const uint32_t q = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
     if (i >= A.ext_n) return;
     const uint32_t mask = A.ext_n - 1, nx = (i + A.step) & mask, pv = (i - A.step) & mask, lastr = (i - (BF + 1) * A.step) & mask;
@@ -440,17 +443,23 @@ __global__ void __launch_bounds__(128, 3) k_quotient(const QuotArgs A, const Dev
     auto ext = [&](int slot, uint32_t idx) { return ldv(A.E + ((size_t)slot * A.QB + q) * A.ext_n + idx); };
     auto fx = [&](int col) { return ldv_nc(A.fixed_c + (size_t)col * A.ext_n + i); };
     auto wy = [&](const fe_t& e, int k) { return Fr::mul(e, ldv_nc(yp + k)); };
-    fe_t col[NPERM];
-    for (int c = 0; c < NADV; c++) col[c] = ext(SL_ADV + c, i);
-    col[NADV] = Fr::zero();
+    // the advice values are re-read where they are used (L1 hits) instead of being held in 40 registers across the kernel
+    auto adv = [&](int c) { return c < NADV ? ext(SL_ADV + c, i) : Fr::zero(); };
     // main gate
-    fe_t gate = Fr::mul(col[0], fx(FX_SA));
-    gate = Fr::add(gate, Fr::mul(col[1], fx(FX_SB)));
-    gate = Fr::add(gate, Fr::mul(col[2], fx(FX_SC)));
-    gate = Fr::add(gate, Fr::mul(col[3], fx(FX_SD)));
-    gate = Fr::add(gate, Fr::mul(col[4], fx(FX_SE)));
-    gate = Fr::add(gate, Fr::mul(Fr::mul(col[0], col[1]), fx(FX_MUL_AB)));
-    gate = Fr::add(gate, Fr::mul(Fr::mul(col[2], col[3]), fx(FX_MUL_CD)));
+    fe_t gate;
+    {
+        const fe_t a = adv(0), b = adv(1);
+        gate = Fr::mul(a, fx(FX_SA));
+        gate = Fr::add(gate, Fr::mul(b, fx(FX_SB)));
+        gate = Fr::add(gate, Fr::mul(Fr::mul(a, b), fx(FX_MUL_AB)));
+    }
+    {
+        const fe_t c = adv(2), d = adv(3);
+        gate = Fr::add(gate, Fr::mul(c, fx(FX_SC)));
+        gate = Fr::add(gate, Fr::mul(d, fx(FX_SD)));
+        gate = Fr::add(gate, Fr::mul(Fr::mul(c, d), fx(FX_MUL_CD)));
+    }
+    gate = Fr::add(gate, Fr::mul(adv(4), fx(FX_SE)));
     gate = Fr::add(gate, Fr::mul(ext(SL_ADV + 4, nx), fx(FX_SE_NEXT)));
     gate = Fr::add(gate, fx(FX_CONST));
     fe_t acc = wy(gate, 0);
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(128, 3) k_quotient(const QuotArgs A, const Dev
     for (int s = 0; s < NSETS; s++) {
         fe_t left = ext(SL_PZ + s, nx), right = pz[s];
         for (int c = s * CHUNK; c < (s + 1) * CHUNK && c < NPERM; c++) {
-            const fe_t vg = Fr::add(col[c], gamma);
+            const fe_t vg = Fr::add(adv(c), gamma);
             left = Fr::mul(left, Fr::add(Fr::mul(beta, ldv_nc(A.sigma_c + (size_t)c * A.ext_n + i)), vg));
             right = Fr::mul(right, Fr::add(Fr::mul(beta_x, C.delta_pows[c]), vg));
         }
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(128, 3) k_quotient(const QuotArgs A, const Dev
         const int k0 = 4 + NSETS + 5 * l;
         const fe_t z = ext(SL_LZ + l, i), zn = ext(SL_LZ + l, nx), ap = ext(SL_LA + 2 * l, i), sp = ext(SL_LA + 2 * l + 1, i),
                    apv = ext(SL_LA + 2 * l, pv);
-        const fe_t inp = l < 4 ? Fr::add(tag_c, Fr::mul(s_c, col[l])) : Fr::add(tag_o, Fr::mul(s_o, col[0]));
+        const fe_t inp = l < 4 ? Fr::add(tag_c, Fr::mul(s_c, adv(l))) : Fr::add(tag_o, Fr::mul(s_o, adv(0)));
         g0 = Fr::add(g0, wy(Fr::sub(one, z), k0));
         glast = Fr::add(glast, wy(Fr::sub(Fr::sqr(z), z), k0 + 1));
         const fe_t left = Fr::mul(Fr::mul(zn, Fr::add(ap, beta)), Fr::add(sp, gamma));
