@@ -58,6 +58,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_msm_g1": [vp, vp, vp, sz, vp],
         "b2r_msm_g1_batch": [vp, vp, vp, sz, sz, vp],
         "b2r_msm_g1_batch_dev": [vp, vp, vp, sz, sz, vp],
+        "b2r_msm_g1_batch_dev_ex": [vp, vp, vp, sz, sz, u32, vp],
         "b2r_profile_enable": [vp, i32],
         "b2r_profile_read": [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(C.c_double)],
         "b2r_profile_dump": [vp, C.c_char_p, sz, i32],
@@ -242,8 +243,14 @@ class Context:
         self._ck(self.lib.b2r_msm_g1_batch(self.h, bases.h, _host_ptr(scalars), m, n, _host_ptr(out)))
         return out
 
-    def msm_batch_dev(self, bases: "Bases", scalars_dptr: int, m: int, n: int, out_dptr: int):
-        self._ck(self.lib.b2r_msm_g1_batch_dev(self.h, bases.h, C.c_void_p(scalars_dptr), m, n, C.c_void_p(out_dptr)))
+    MSM_UNIFORM = 1
+
+    def msm_batch_dev(self, bases: "Bases", scalars_dptr: int, m: int, n: int, out_dptr: int, uniform: bool = False):
+        """device-resident scalars / outputs; uniform=True passes B2R_MSM_UNIFORM (binned counting sort, same result)"""
+        if uniform:
+            self._ck(self.lib.b2r_msm_g1_batch_dev_ex(self.h, bases.h, C.c_void_p(scalars_dptr), m, n, self.MSM_UNIFORM, C.c_void_p(out_dptr)))
+        else:
+            self._ck(self.lib.b2r_msm_g1_batch_dev(self.h, bases.h, C.c_void_p(scalars_dptr), m, n, C.c_void_p(out_dptr)))
 
     def srs_setup(self, k: int, secret: np.ndarray):
         """ParamsKZG::setup(k) for a chosen secret (uint64[4] Montgomery) -> (g, g_lagrange)"""

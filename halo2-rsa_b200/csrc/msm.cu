@@ -968,6 +968,16 @@ int32_t b2r_msm_g1_batch_dev(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr*
     return msm_batch_dev(ctx, bases, (const fe_t*)scalars_dev, m, n, (affine_t*)out_dev, false);
 }
 
+int32_t b2r_msm_g1_batch_dev_ex(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars_dev, size_t m, size_t n, uint32_t flags,
+                                b2r_g1_affine* out_dev) {
+    if (!ctx) return B2R_ERR_INVALID;
+    if (!bases || !out_dev || (!scalars_dev && n)) return fail(ctx, B2R_ERR_INVALID, "msm: null pointer");
+    if (flags & ~B2R_MSM_UNIFORM) return fail(ctx, B2R_ERR_INVALID, "msm: unknown flag");
+    if (n > bases->n) return fail(ctx, B2R_ERR_INVALID, "msm: more scalars than registered bases");
+    if (m == 0) return 0;
+    return msm_batch_dev(ctx, bases, (const fe_t*)scalars_dev, m, n, (affine_t*)out_dev, (flags & B2R_MSM_UNIFORM) != 0);
+}
+
 int32_t b2r_msm_g1_batch(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars, size_t m, size_t n,
                          b2r_g1_affine* out) {
     if (!ctx) return B2R_ERR_INVALID;

@@ -116,6 +116,14 @@ int32_t b2r_msm_g1_batch(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* sca
                          size_t n, b2r_g1_affine* out);
 int32_t b2r_msm_g1_batch_dev(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars_dev,
                              size_t m, size_t n, b2r_g1_affine* out_dev);
+/* The same with a caller's hint.  B2R_MSM_UNIFORM: the non-zero scalars are (pseudo-)random field elements - quotient
+ * pieces, opening witnesses, blinded polynomials in coefficient form, i.e. what create_proof hands to ParamsKZG::commit
+ * (benches/bench.rs:321-329) - so their digits fill the buckets evenly and the entries are sorted by the two-pass
+ * binned counting sort instead of per-entry atomics (4x faster sort).  The hint never changes the result: a vector
+ * that turns out not to be uniform overflows a bin, which is detected, and the call falls back to the general path. */
+#define B2R_MSM_UNIFORM 1u
+int32_t b2r_msm_g1_batch_dev_ex(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars_dev,
+                                size_t m, size_t n, uint32_t flags, b2r_g1_affine* out_dev);
 
 /* copies the registered affine points (window 0 of the table) back to the host */
 int32_t b2r_bases_download(b2r_ctx* ctx, const b2r_bases* bases, b2r_g1_affine* out_host, size_t n);

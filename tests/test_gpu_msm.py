@@ -107,3 +107,24 @@ def test_msm_binned_sort_path(ctx, log_n, monkeypatch):
         k = (v[0] * tri if j == 2 else sum(s * (i + 1) for i, s in enumerate(v))) % O.R_MOD
         assert got[j] == O.g1_mul(O.G1_GEN, k), f"vector {j}"
     bs.free()
+
+
+def test_msm_uniform_hint_same_result(ctx):
+    """b2r_msm_g1_batch_dev_ex with B2R_MSM_UNIFORM: identical commitments for uniform vectors (binned sort) and for a
+    skewed vector that overflows a bin (detected, general path)"""
+    import torch
+    n = 1 << 15       # > 2^14 so that the table has 16-bit windows (the binned sort's width)
+    pts = O.g1_multiples(n)
+    bs = ctx.bases_register(g1_to_np(pts))
+    vecs = [O.fr_stream(0xC1, n), [(7 if i % 3 else 0) for i in range(n)]]
+    arr = torch.from_numpy(np.stack([fr_to_np(v) for v in vecs]).view(np.int64)).cuda()
+    out_a = torch.zeros(2 * 8, dtype=torch.int64, device="cuda")
+    out_b = torch.zeros(2 * 8, dtype=torch.int64, device="cuda")
+    ctx.msm_batch_dev(bs, arr.data_ptr(), 2, n, out_a.data_ptr())
+    ctx.msm_batch_dev(bs, arr.data_ptr(), 2, n, out_b.data_ptr(), uniform=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out_a, out_b)
+    got = np_to_g1(out_b.cpu().numpy().view(np.uint64).reshape(2, 8))
+    for j, v in enumerate(vecs):
+        assert got[j] == O.g1_mul(O.G1_GEN, sum(s * (i + 1) for i, s in enumerate(v)) % O.R_MOD)
+    bs.free()

@@ -58,15 +58,15 @@ def main():
         print(f"msm 2^{L}: bases gen {t1-t0:.1f}s register {t2-t1:.2f}s", flush=True)
         sc = torch.from_numpy(random_fr_np(n, 0x5EED).view(np.int64)).cuda()
         out = torch.zeros(8 * a.batch, dtype=torch.int64, device="cuda")
-        best, avg = timeit(lambda: ctx.msm_batch_dev(bs, sc.data_ptr(), 1, n, out.data_ptr()))
+        best, avg = timeit(lambda: ctx.msm_batch_dev(bs, sc.data_ptr(), 1, n, out.data_ptr(), uniform=True))
         gb = n * 96 / 1e9
         print(f"msm 2^{L} uniform: best {best:.3f} ms avg {avg:.3f} -> {gb/best*1e3:.1f} GB/s algorithmic", flush=True)
         if L <= 17:
             scb = torch.from_numpy(random_fr_np(n * a.batch, 7).view(np.int64)).cuda()
-            best, avg = timeit(lambda: ctx.msm_batch_dev(bs, scb.data_ptr(), a.batch, n, out.data_ptr()))
+            best, avg = timeit(lambda: ctx.msm_batch_dev(bs, scb.data_ptr(), a.batch, n, out.data_ptr(), uniform=True))
             print(f"msm 2^{L} x{a.batch} uniform: best {best:.3f} ms ({best/a.batch:.3f} each)", flush=True)
             ctx.profile_enable(True); ctx.profile_dump(clear=True)
-            ctx.msm_batch_dev(bs, scb.data_ptr(), a.batch, n, out.data_ptr())
+            ctx.msm_batch_dev(bs, scb.data_ptr(), a.batch, n, out.data_ptr(), uniform=True)
             print("   per kernel (ms):", {k: round(v[0], 3) for k, v in ctx.profile_dump(clear=True).items()}, flush=True)
             ctx.profile_enable(False)
             # advice-like skew: 40% zero, 30% one, 20% bytes, 9% 64-bit, 1% full
