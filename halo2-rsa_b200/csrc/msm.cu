@@ -239,7 +239,11 @@ k_digits(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, uint32_
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
     fe_t s = Fr::zero();
-    if (live) s = Fr::from_mont(ldg_fe(scalars + (size_t)g * n + i));
+    if (live) s = ldg_fe(scalars + (size_t)g * n + i);
+    // the sparse columns this kernel serves (first differences of A', S', unused advice rows) are mostly zero: a warp
+    // whose 32 scalars are all zero has nothing to convert or emit (the whole warp leaves: the votes below stay complete)
+    if (__all_sync(0xffffffffu, Fr::is_zero(s))) return;
+    s = Fr::from_mont(s);
     uint32_t* cnt = counts + (size_t)g * B;
     uint32_t* ent = SCATTER ? entries + (size_t)g * ent_stride : nullptr;
     uint32_t* key = SCATTER ? keys + (size_t)g * ent_stride : nullptr;
@@ -307,10 +311,17 @@ k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, ui
     if (tid < HI) hist[tid] = 0;
     __syncthreads();
     fe_t s = Fr::zero();
-    if (i < n) s = Fr::from_mont(ldg_fe(scalars + (size_t)g * n + i));
+    if (i < n) s = ldg_fe(scalars + (size_t)g * n + i);
     uint32_t packed[W], where[W];   // where = hi << 16 | rank inside the CTA's share of the bin; 0xffffffff = no entry
-    uint32_t carry = 0;
-    DigitLoopBins<C, 0, W, C - 1 - HB>::run(s, carry, i, n_table, idx_bits, hist, packed, where);
+    // the grand-product differences are zero on most rows: a warp of 32 zero scalars skips the conversion and the digits
+    if (__all_sync(0xffffffffu, Fr::is_zero(s))) {
+#pragma unroll
+        for (int j = 0; j < W; j++) { packed[j] = 0; where[j] = 0xffffffffu; }
+    } else {
+        s = Fr::from_mont(s);
+        uint32_t carry = 0;
+        DigitLoopBins<C, 0, W, C - 1 - HB>::run(s, carry, i, n_table, idx_bits, hist, packed, where);
+    }
     __syncthreads();
     if (tid < HI) base[tid] = hist[tid] ? atomicAdd(&bin_fill[(size_t)g * HI + tid], hist[tid]) : 0;
     if (wid == 7) {   // exclusive scan of the local counts by one warp, PER bins per lane
