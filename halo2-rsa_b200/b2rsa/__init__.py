@@ -80,6 +80,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_pk_export_vk": [vp, vp, vp, vp],
         "b2r_rsa_prove_batch": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
         "b2r_rsa_prove_batch_dev": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
+        "b2r_rsa_prove_batch_ex": [vp, vp, vp, vp, vp, sz, vp, u64, u32, vp, vp],
+        "b2r_pk_set_transcript_repr": [vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the ABI symbol is missing: loud by design
@@ -343,8 +345,15 @@ class ProvingKey:
         self.ctx._ck(self.ctx.lib.b2r_pk_export_vk(self.h, _host_ptr(f), _host_ptr(s), _host_ptr(t)))
         return f, s, t
 
-    def prove_batch(self, n_limbs, sig_limbs, hash_limbs, seed: int):
-        """create_proof for a batch -> (proofs uint8[batch, proof_bytes], status uint8[batch])"""
+    def set_transcript_repr(self, repr_limbs):
+        """install the Rust verifying key's transcript_repr (uint64[4], reduced Montgomery limbs)"""
+        t = np.ascontiguousarray(repr_limbs, dtype=np.uint64).reshape(4)
+        self.ctx._ck(self.ctx.lib.b2r_pk_set_transcript_repr(self.h, _host_ptr(t)))
+
+    def prove_batch(self, n_limbs, sig_limbs, hash_limbs, seed, nonce: int | None = None):
+        """create_proof for a batch -> (proofs uint8[batch, proof_bytes], status uint8[batch]).
+        seed: int (64-bit test seed) or 32 bytes (the ChaCha20 key).  nonce=None with an int seed calls the plain
+        entry point (the context supplies a fresh nonce per call); an explicit nonce makes the call reproducible."""
         n_limbs = np.ascontiguousarray(n_limbs, dtype=np.uint64)
         sig_limbs = np.ascontiguousarray(sig_limbs, dtype=np.uint64)
         hash_limbs = np.ascontiguousarray(hash_limbs, dtype=np.uint64)
@@ -352,11 +361,26 @@ class ProvingKey:
         proofs = np.zeros((batch, self.proof_bytes), dtype=np.uint8)
         status = np.zeros(batch, dtype=np.uint8)
         self.prove_batch_raw(n_limbs.ctypes.data, sig_limbs.ctypes.data, hash_limbs.ctypes.data, batch, seed, proofs.ctypes.data,
-                             status.ctypes.data)
+                             status.ctypes.data, nonce=nonce)
         return proofs, status
 
-    def prove_batch_raw(self, n_ptr: int, s_ptr: int, h_ptr: int, batch: int, seed: int, proofs_ptr: int, status_ptr: int,
-                        inputs_on_device: bool = False):
+    PROVE_INPUTS_ON_DEVICE, PROVE_SEED64 = 1, 2
+
+    def prove_batch_raw(self, n_ptr: int, s_ptr: int, h_ptr: int, batch: int, seed, proofs_ptr: int, status_ptr: int,
+                        inputs_on_device: bool = False, nonce: int | None = None):
+        if nonce is not None or isinstance(seed, (bytes, bytearray)):
+            flags = self.PROVE_INPUTS_ON_DEVICE if inputs_on_device else 0
+            if isinstance(seed, (bytes, bytearray)):
+                if len(seed) != 32:
+                    raise ValueError("seed bytes must be the 32-byte ChaCha20 key")
+                key = bytes(seed)
+            else:
+                key = int(seed).to_bytes(8, "little") + bytes(24)
+                flags |= self.PROVE_SEED64
+            kb = (C.c_uint8 * 32).from_buffer_copy(key)
+            self.ctx._ck(self.ctx.lib.b2r_rsa_prove_batch_ex(self.ctx.h, self.h, C.c_void_p(n_ptr), C.c_void_p(s_ptr), C.c_void_p(h_ptr), batch,
+                                                            C.cast(kb, C.c_void_p), nonce or 0, flags, C.c_void_p(proofs_ptr), C.c_void_p(status_ptr)))
+            return
         fn = self.ctx.lib.b2r_rsa_prove_batch_dev if inputs_on_device else self.ctx.lib.b2r_rsa_prove_batch
         self.ctx._ck(fn(self.ctx.h, self.h, C.c_void_p(n_ptr), C.c_void_p(s_ptr), C.c_void_p(h_ptr), batch,
                seed, C.c_void_p(proofs_ptr), C.c_void_p(status_ptr)))

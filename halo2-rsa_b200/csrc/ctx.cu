@@ -94,8 +94,8 @@ int32_t b2r_ctx_destroy(b2r_ctx* ctx) {
     return 0;
 }
 
-int32_t b2r_ctx_set_stream(b2r_ctx* ctx, void* cuda_stream) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_ctx_set_stream(b2r_ctx* ctx, void* cuda_stream) try {
+    B2R_ENTER(ctx);
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (cuda_stream) {
@@ -106,13 +106,13 @@ int32_t b2r_ctx_set_stream(b2r_ctx* ctx, void* cuda_stream) {
         ctx->own_stream = true;
     }
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
-int32_t b2r_ctx_sync(b2r_ctx* ctx) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_ctx_sync(b2r_ctx* ctx) try {
+    B2R_ENTER(ctx);
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 const char* b2r_last_error(const b2r_ctx* ctx) {
     if (!ctx) return g_create_err.c_str();
@@ -121,14 +121,15 @@ const char* b2r_last_error(const b2r_ctx* ctx) {
 
 uint64_t b2r_launch_count(const b2r_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int32_t b2r_profile_enable(b2r_ctx* ctx, int32_t on) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_profile_enable(b2r_ctx* ctx, int32_t on) try {
+    B2R_ENTER(ctx);
     ctx->profile = on != 0;
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 // sums the recorded launches whose name matches `name` exactly; clears nothing
-int32_t b2r_profile_read(b2r_ctx* ctx, const char* name, double* total_ms, uint64_t* launches, double* units) {
+int32_t b2r_profile_read(b2r_ctx* ctx, const char* name, double* total_ms, uint64_t* launches, double* units) try {
+    B2R_ENTER(ctx);
     if (!ctx || !name) return B2R_ERR_INVALID;
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double ms = 0, u = 0;
@@ -145,10 +146,11 @@ int32_t b2r_profile_read(b2r_ctx* ctx, const char* name, double* total_ms, uint6
     if (launches) *launches = cnt;
     if (units) *units = u;
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 // writes "name:ms:launches;..." for every distinct name, then clears the records
-int32_t b2r_profile_dump(b2r_ctx* ctx, char* buf, size_t cap, int32_t clear) {
+int32_t b2r_profile_dump(b2r_ctx* ctx, char* buf, size_t cap, int32_t clear) try {
+    B2R_ENTER(ctx);
     if (!ctx || !buf || cap == 0) return B2R_ERR_INVALID;
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::map<std::string, std::pair<double, uint64_t>> acc;
@@ -175,30 +177,31 @@ int32_t b2r_profile_dump(b2r_ctx* ctx, char* buf, size_t cap, int32_t clear) {
         ctx->prof.clear();
     }
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
-int32_t b2r_dev_alloc(b2r_ctx* ctx, size_t bytes, void** dptr) {
+int32_t b2r_dev_alloc(b2r_ctx* ctx, size_t bytes, void** dptr) try {
+    B2R_ENTER(ctx);
     if (!ctx || !dptr) return B2R_ERR_INVALID;
     B2R_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
     return 0;
-}
-int32_t b2r_dev_free(b2r_ctx* ctx, void* dptr) {
-    if (!ctx) return B2R_ERR_INVALID;
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_dev_free(b2r_ctx* ctx, void* dptr) try {
+    B2R_ENTER(ctx);
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     B2R_CUDA(ctx, cudaFree(dptr));
     return 0;
-}
-int32_t b2r_h2d(b2r_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
-    if (!ctx) return B2R_ERR_INVALID;
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_h2d(b2r_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) try {
+    B2R_ENTER(ctx);
     B2R_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
-}
-int32_t b2r_d2h(b2r_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
-    if (!ctx) return B2R_ERR_INVALID;
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_d2h(b2r_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) try {
+    B2R_ENTER(ctx);
     B2R_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 }  // extern "C"

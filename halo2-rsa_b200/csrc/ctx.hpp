@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <map>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -43,6 +45,7 @@ struct b2r_ctx {
     bool own_stream = true;
     std::string err;
     uint64_t launches = 0;
+    uint64_t prove_calls = 0;  // nonce of the 64-bit-seed prove entry points: one blinding stream per call
     // twiddle tables: omega^e, e < n/2, Montgomery form, device resident
     std::map<b2r::TwiddleKey, b2r::fe_t*> twiddles;
     // grow-only scratch arenas (ping-pong buffers, MSM work arrays, staging)
@@ -61,6 +64,33 @@ int32_t fail(b2r_ctx* ctx, int32_t code, const std::string& msg);
 int32_t cuda_fail(b2r_ctx* ctx, cudaError_t e, const char* what);
 // returns device pointer of at least `bytes` from arena `slot` (contents undefined)
 int32_t scratch_get(b2r_ctx* ctx, int slot, size_t bytes, void** out);
+
+// Every ABI entry point runs on ITS context's device whatever the calling thread's current device is (a host that
+// keeps one context per GPU in one process - INTEGRATION.md section 4 - must not have to cudaSetDevice itself), and
+// restores the caller's device on the way out.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess || prev != device) {
+            cudaSetDevice(device);
+            switched = prev >= 0;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define B2R_ENTER(ctx)                        \
+    if (!(ctx)) return B2R_ERR_INVALID;       \
+    b2r::DeviceGuard _b2r_device_guard((ctx)->device)
+// the ABI never unwinds into the caller (a Rust / C host): entry points are function-try-blocks closed by this
+#define B2R_ABI_CATCH(ctx)                                                                                   \
+    catch (const std::bad_alloc&) { return b2r::fail((b2r_ctx*)(ctx), B2R_ERR_NOMEM, "out of host memory"); }  \
+    catch (const std::exception& e) { return b2r::fail((b2r_ctx*)(ctx), B2R_ERR_INVALID, e.what()); }          \
+    catch (...) { return b2r::fail((b2r_ctx*)(ctx), B2R_ERR_INVALID, "unknown exception"); }
 
 #define B2R_CUDA(ctx, call)                                          \
     do {                                                             \

@@ -779,11 +779,8 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
         B2R_LAUNCH_CHECK(ctx);
         k_bin_prefix<<<(unsigned)G, BIN_MAX, 0, st>>>(bin_fill, bin_base, off, B, HI);
         B2R_LAUNCH_CHECK(ctx);
-        static bool attr_set = false;
-        if (!attr_set) {
-            B2R_CUDA(ctx, cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BIN_CAP * 4)));
-            attr_set = true;
-        }
+        // function attributes are per device: set on every call (a process may hold one context per GPU)
+        B2R_CUDA(ctx, cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BIN_CAP * 4)));
         k_bin_sort<<<dim3(HI, (unsigned)G), BIN_SORT_T, BIN_CAP * 4, st>>>(bin_data, bin_fill, bin_base, idx_bits, B, HI, off, ent, key, ent_cap);
         B2R_LAUNCH_CHECK(ctx); }
         std::vector<uint32_t> hf(G);
@@ -803,7 +800,7 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     }
     { KTimer kt(ctx, "msm_accum_entries", entries_total);
     {
-        static const char* ov = getenv("B2R_MSM_VARIANT");  // tuning hook (occupancy / prefetch variants)
+        const char* ov = getenv("B2R_MSM_VARIANT");  // tuning hook (occupancy / prefetch variants)
         const int variant = ov ? atoi(ov) : 0;
         const dim3 ga((nch1 + 127) / 128, (unsigned)G);
 #define B2R_ACC(MINB, PF) k_accum_entries<L1, MINB, PF><<<ga, 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa, slotsA)
@@ -903,6 +900,8 @@ int32_t bases_register_dev(b2r_ctx* ctx, const affine_t* d_in, size_t n, b2r_bas
     return 0;
 }
 
+size_t bases_count(const b2r_bases* bs) { return bs ? bs->n : 0; }
+
 void bases_destroy(b2r_bases* bs) {
     if (!bs) return;
     cudaFree(bs->table);
@@ -943,8 +942,8 @@ using namespace b2r;
 
 extern "C" {
 
-int32_t b2r_bases_register(b2r_ctx* ctx, const b2r_g1_affine* bases_host, size_t n, b2r_bases** out) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_bases_register(b2r_ctx* ctx, const b2r_g1_affine* bases_host, size_t n, b2r_bases** out) try {
+    B2R_ENTER(ctx);
     if (!bases_host || !out || n == 0) return fail(ctx, B2R_ERR_INVALID, "bases_register: bad argument");
     if (n > ((size_t)1 << 26)) return fail(ctx, B2R_ERR_INVALID, "bases_register: n > 2^26");
     *out = nullptr;
@@ -952,46 +951,47 @@ int32_t b2r_bases_register(b2r_ctx* ctx, const b2r_g1_affine* bases_host, size_t
     B2R_TRY(scratch_get(ctx, SC_STAGE, n * sizeof(affine_t), (void**)&d_in));
     B2R_CUDA(ctx, cudaMemcpyAsync(d_in, bases_host, n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
     return bases_register_dev(ctx, d_in, n, out, 0);
-}
+} B2R_ABI_CATCH(ctx)
 
-int32_t b2r_bases_download(b2r_ctx* ctx, const b2r_bases* bases, b2r_g1_affine* out_host, size_t n) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_bases_download(b2r_ctx* ctx, const b2r_bases* bases, b2r_g1_affine* out_host, size_t n) try {
+    B2R_ENTER(ctx);
     if (!bases || !out_host || n > bases->n) return fail(ctx, B2R_ERR_INVALID, "bases_download: bad argument");
     B2R_CUDA(ctx, cudaMemcpyAsync(out_host, bases->table, n * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
-int32_t b2r_bases_free(b2r_ctx* ctx, b2r_bases* bases) {
+int32_t b2r_bases_free(b2r_ctx* ctx, b2r_bases* bases) try {
+    B2R_ENTER(ctx);
     if (!ctx || !bases) return B2R_ERR_INVALID;
     cudaStreamSynchronize(ctx->stream);
     cudaFree(bases->table);
     delete bases;
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 int32_t b2r_msm_g1_batch_dev(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars_dev, size_t m, size_t n,
-                             b2r_g1_affine* out_dev) {
-    if (!ctx) return B2R_ERR_INVALID;
+                             b2r_g1_affine* out_dev) try {
+    B2R_ENTER(ctx);
     if (!bases || !out_dev || (!scalars_dev && n)) return fail(ctx, B2R_ERR_INVALID, "msm: null pointer");
     if (n > bases->n) return fail(ctx, B2R_ERR_INVALID, "msm: more scalars than registered bases");
     if (m == 0) return 0;
     return msm_batch_dev(ctx, bases, (const fe_t*)scalars_dev, m, n, (affine_t*)out_dev, false);
-}
+} B2R_ABI_CATCH(ctx)
 
 int32_t b2r_msm_g1_batch_dev_ex(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars_dev, size_t m, size_t n, uint32_t flags,
-                                b2r_g1_affine* out_dev) {
-    if (!ctx) return B2R_ERR_INVALID;
+                                b2r_g1_affine* out_dev) try {
+    B2R_ENTER(ctx);
     if (!bases || !out_dev || (!scalars_dev && n)) return fail(ctx, B2R_ERR_INVALID, "msm: null pointer");
     if (flags & ~B2R_MSM_UNIFORM) return fail(ctx, B2R_ERR_INVALID, "msm: unknown flag");
     if (n > bases->n) return fail(ctx, B2R_ERR_INVALID, "msm: more scalars than registered bases");
     if (m == 0) return 0;
     return msm_batch_dev(ctx, bases, (const fe_t*)scalars_dev, m, n, (affine_t*)out_dev, (flags & B2R_MSM_UNIFORM) != 0);
-}
+} B2R_ABI_CATCH(ctx)
 
 int32_t b2r_msm_g1_batch(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars, size_t m, size_t n,
-                         b2r_g1_affine* out) {
-    if (!ctx) return B2R_ERR_INVALID;
+                         b2r_g1_affine* out) try {
+    B2R_ENTER(ctx);
     if (!bases || !out || (!scalars && n)) return fail(ctx, B2R_ERR_INVALID, "msm: null pointer");
     if (n > bases->n) return fail(ctx, B2R_ERR_INVALID, "msm: more scalars than registered bases");
     if (m == 0) return 0;
@@ -1004,10 +1004,10 @@ int32_t b2r_msm_g1_batch(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* sca
     B2R_CUDA(ctx, cudaMemcpyAsync(out, d + sb_al, m * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
-int32_t b2r_msm_g1(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars, size_t n, b2r_g1* out) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_msm_g1(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars, size_t n, b2r_g1* out) try {
+    B2R_ENTER(ctx);
     if (!out) return fail(ctx, B2R_ERR_INVALID, "msm: null pointer");
     b2r_g1_affine a;
     B2R_TRY(b2r_msm_g1_batch(ctx, bases, scalars, 1, n, &a));
@@ -1025,6 +1025,6 @@ int32_t b2r_msm_g1(b2r_ctx* ctx, const b2r_bases* bases, const b2r_fr* scalars, 
         out->z = one64;
     }
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 }  // extern "C"

@@ -346,7 +346,7 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         // (tools/microbench.py, B2R_NTT_LOGC sweep)
         uint32_t log_c = (S[p] >= 8) ? 2 : (S[p] == 7 ? 3 : 4);
         {   // tuning hook (tools/microbench.py): columns per CTA
-            static const char* ov = getenv("B2R_NTT_LOGC");
+            const char* ov = getenv("B2R_NTT_LOGC");
             if (ov) log_c = (uint32_t)atoi(ov);
             if ((((size_t)sizeof(fe_t) << S[p]) << log_c) > 200 * 1024) log_c = 2;
         }
@@ -407,63 +407,64 @@ using namespace b2r;
 
 extern "C" {
 
-int32_t b2r_ntt_fr(b2r_ctx* ctx, b2r_fr* a, const b2r_fr* omega, uint32_t log_n) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_ntt_fr(b2r_ctx* ctx, b2r_fr* a, const b2r_fr* omega, uint32_t log_n) try {
+    B2R_ENTER(ctx);
     if (!a || !omega) return fail(ctx, B2R_ERR_INVALID, "ntt: null pointer");
     if (log_n > 27) return fail(ctx, B2R_ERR_INVALID, "ntt: log_n > 27");
     return ntt_host(ctx, a, 1u << log_n, a, fe_from_abi(omega), log_n, MODE_PLAIN);
-}
-int32_t b2r_ntt_fr_dev(b2r_ctx* ctx, b2r_fr* a_dev, const b2r_fr* omega_host, uint32_t log_n) {
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_ntt_fr_dev(b2r_ctx* ctx, b2r_fr* a_dev, const b2r_fr* omega_host, uint32_t log_n) try {
+    B2R_ENTER(ctx);
     return b2r_ntt_fr_batch_dev(ctx, a_dev, 1, omega_host, log_n);
-}
-int32_t b2r_ntt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, const b2r_fr* omega_host, uint32_t log_n) {
-    if (!ctx) return B2R_ERR_INVALID;
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_ntt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, const b2r_fr* omega_host, uint32_t log_n) try {
+    B2R_ENTER(ctx);
     if (!a_dev || !omega_host) return fail(ctx, B2R_ERR_INVALID, "ntt: null pointer");
     uint64_t n = 1ull << log_n;
     return ntt_run(ctx, (fe_t*)a_dev, n, (uint32_t)n, (fe_t*)a_dev, n, batch, fe_from_abi(omega_host), log_n, MODE_PLAIN);
-}
-int32_t b2r_intt_fr(b2r_ctx* ctx, b2r_fr* a, uint32_t k) {
-    if (!ctx) return B2R_ERR_INVALID;
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_intt_fr(b2r_ctx* ctx, b2r_fr* a, uint32_t k) try {
+    B2R_ENTER(ctx);
     if (!a) return fail(ctx, B2R_ERR_INVALID, "intt: null pointer");
     if (k > 27) return fail(ctx, B2R_ERR_INVALID, "intt: k > 27");
     return ntt_host(ctx, a, 1u << k, a, Fr::inv(fr_omega(k)), k, MODE_INV);
-}
-int32_t b2r_intt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, uint32_t k) {
-    if (!ctx) return B2R_ERR_INVALID;
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_intt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, uint32_t k) try {
+    B2R_ENTER(ctx);
     if (!a_dev) return fail(ctx, B2R_ERR_INVALID, "intt: null pointer");
     if (k > 27) return fail(ctx, B2R_ERR_INVALID, "intt: k > 27");
     uint64_t n = 1ull << k;
     return ntt_run(ctx, (fe_t*)a_dev, n, (uint32_t)n, (fe_t*)a_dev, n, batch, Fr::inv(fr_omega(k)), k, MODE_INV);
-}
-int32_t b2r_coset_ntt_fr(b2r_ctx* ctx, const b2r_fr* coeffs, uint32_t k, uint32_t ext_k, b2r_fr* out) {
-    if (!ctx) return B2R_ERR_INVALID;
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_coset_ntt_fr(b2r_ctx* ctx, const b2r_fr* coeffs, uint32_t k, uint32_t ext_k, b2r_fr* out) try {
+    B2R_ENTER(ctx);
     if (!coeffs || !out) return fail(ctx, B2R_ERR_INVALID, "coset_ntt: null pointer");
     if (ext_k > 27 || k > ext_k) return fail(ctx, B2R_ERR_INVALID, "coset_ntt: need k <= ext_k <= 27");
     return ntt_host(ctx, coeffs, 1u << k, out, fr_omega(ext_k), ext_k, MODE_COSET_FWD);
-}
+} B2R_ABI_CATCH(ctx)
 int32_t b2r_coset_ntt_fr_batch_dev(b2r_ctx* ctx, const b2r_fr* coeffs_dev, size_t batch, uint32_t k, uint32_t ext_k,
-                                   b2r_fr* out_dev) {
-    if (!ctx) return B2R_ERR_INVALID;
+                                   b2r_fr* out_dev) try {
+    B2R_ENTER(ctx);
     if (!coeffs_dev || !out_dev) return fail(ctx, B2R_ERR_INVALID, "coset_ntt: null pointer");
     if (ext_k > 27 || k > ext_k) return fail(ctx, B2R_ERR_INVALID, "coset_ntt: need k <= ext_k <= 27");
     if ((const void*)coeffs_dev == (void*)out_dev && k != ext_k)
         return fail(ctx, B2R_ERR_INVALID, "coset_ntt: in place needs k == ext_k");
     return ntt_run(ctx, (const fe_t*)coeffs_dev, 1ull << k, 1u << k, (fe_t*)out_dev, 1ull << ext_k, batch,
                    fr_omega(ext_k), ext_k, MODE_COSET_FWD);
-}
-int32_t b2r_coset_intt_fr(b2r_ctx* ctx, b2r_fr* a, uint32_t ext_k) {
-    if (!ctx) return B2R_ERR_INVALID;
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_coset_intt_fr(b2r_ctx* ctx, b2r_fr* a, uint32_t ext_k) try {
+    B2R_ENTER(ctx);
     if (!a) return fail(ctx, B2R_ERR_INVALID, "coset_intt: null pointer");
     if (ext_k > 27) return fail(ctx, B2R_ERR_INVALID, "coset_intt: ext_k > 27");
     return ntt_host(ctx, a, 1u << ext_k, a, Fr::inv(fr_omega(ext_k)), ext_k, MODE_COSET_INV);
-}
-int32_t b2r_coset_intt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, uint32_t ext_k) {
-    if (!ctx) return B2R_ERR_INVALID;
+} B2R_ABI_CATCH(ctx)
+int32_t b2r_coset_intt_fr_batch_dev(b2r_ctx* ctx, b2r_fr* a_dev, size_t batch, uint32_t ext_k) try {
+    B2R_ENTER(ctx);
     if (!a_dev) return fail(ctx, B2R_ERR_INVALID, "coset_intt: null pointer");
     if (ext_k > 27) return fail(ctx, B2R_ERR_INVALID, "coset_intt: ext_k > 27");
     uint64_t n = 1ull << ext_k;
     return ntt_run(ctx, (fe_t*)a_dev, n, (uint32_t)n, (fe_t*)a_dev, n, batch, Fr::inv(fr_omega(ext_k)), ext_k,
                    MODE_COSET_INV);
-}
+} B2R_ABI_CATCH(ctx)
 
 }  // extern "C"

@@ -62,8 +62,8 @@ using namespace b2r;
 
 extern "C" {
 
-int32_t b2r_srs_setup(b2r_ctx* ctx, uint32_t k, const b2r_fr* secret, b2r_bases** g, b2r_bases** g_lagrange) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_srs_setup(b2r_ctx* ctx, uint32_t k, const b2r_fr* secret, b2r_bases** g, b2r_bases** g_lagrange) try {
+    B2R_ENTER(ctx);
     if (!secret || (!g && !g_lagrange)) return fail(ctx, B2R_ERR_INVALID, "srs_setup: null argument");
     if (k > 24) return fail(ctx, B2R_ERR_INVALID, "srs_setup: k > 24");
     const uint32_t n = 1u << k;
@@ -90,13 +90,13 @@ int32_t b2r_srs_setup(b2r_ctx* ctx, uint32_t k, const b2r_fr* secret, b2r_bases*
         B2R_TRY(b2r_bases_register(ctx, (const b2r_g1_affine*)host.data(), n, dst));
     }
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 int32_t b2r_rsa_commit_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g_lagrange, const uint64_t* n_limbs_dev,
                                  const uint64_t* sig_limbs_dev, const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed,
                                  uint32_t k, uint32_t ext_k, b2r_fr* advice_dev, b2r_fr* ext_dev, b2r_g1_affine* commitments_dev,
-                                 uint8_t* is_valid_dev) {
-    if (!ctx) return B2R_ERR_INVALID;
+                                 uint8_t* is_valid_dev) try {
+    B2R_ENTER(ctx);
     if (!prog || !g_lagrange || !advice_dev || !commitments_dev || !is_valid_dev) return fail(ctx, B2R_ERR_INVALID, "rsa_commit: null pointer");
     const size_t n = (size_t)1 << k;
     // (a) witness: 5 advice columns per instance, Lagrange basis, Montgomery form
@@ -109,12 +109,12 @@ int32_t b2r_rsa_commit_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const b2r_b
         B2R_TRY(b2r_coset_ntt_fr_batch_dev(ctx, advice_dev, batch * 5, k, ext_k, ext_dev));
     }
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 int32_t b2r_rsa_commit_batch(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g_lagrange, const uint64_t* n_limbs,
                              const uint64_t* sig_limbs, const uint64_t* hash_limbs, size_t batch, uint64_t blind_seed, uint32_t k,
-                             uint32_t ext_k, b2r_fr* advice_dev, b2r_fr* ext_dev, b2r_g1_affine* commitments, uint8_t* is_valid) {
-    if (!ctx) return B2R_ERR_INVALID;
+                             uint32_t ext_k, b2r_fr* advice_dev, b2r_fr* ext_dev, b2r_g1_affine* commitments, uint8_t* is_valid) try {
+    B2R_ENTER(ctx);
     if (!prog || !g_lagrange || !n_limbs || !sig_limbs || !hash_limbs || !advice_dev || !commitments || !is_valid)
         return fail(ctx, B2R_ERR_INVALID, "rsa_commit: null pointer");
     if (batch == 0) return 0;
@@ -138,6 +138,6 @@ int32_t b2r_rsa_commit_batch(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases
     B2R_CUDA(ctx, cudaMemcpyAsync(is_valid, d_valid, batch, cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 }  // extern "C"

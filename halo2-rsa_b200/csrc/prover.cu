@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <thread>
 #include <cstring>
 #include <vector>
@@ -39,8 +40,9 @@ int32_t bases_register_rewindowed(b2r_ctx* ctx, const b2r_bases* src, uint32_t w
 int32_t coset_ntt_grouped_dev(b2r_ctx* ctx, const fe_t* coeffs, size_t outer, uint64_t outer_stride, size_t inner, uint32_t k, uint32_t ext_k,
                               fe_t* out);
 void bases_destroy(b2r_bases* bs);
+size_t bases_count(const b2r_bases* bs);
 int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
-                    const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev, uint8_t* is_valid_dev,
+                    const uint64_t* hash_limbs_dev, size_t batch, const BlindKey& bkey, b2r_fr* advice_dev, uint8_t* is_valid_dev,
                     size_t p_base, size_t p_stride, size_t col_stride);
 }  // namespace b2r
 
@@ -236,7 +238,7 @@ k_lookup_plan(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ or
 
 __global__ void __launch_bounds__(256)
 k_lookup_fill(fe_t* __restrict__ P, const LookupPlan* __restrict__ plans, const fe_t* __restrict__ sorted_cv, uint32_t T, uint32_t n,
-              uint32_t u, uint32_t B, uint64_t seed, uint32_t p_base) {
+              uint32_t u, uint32_t B, const BlindKey seed, uint32_t p_base) {
     const uint32_t li = blockIdx.y, p = blockIdx.z, row = blockIdx.x * 256 + threadIdx.x;
     if (row >= n) return;
     fe_t* outA = P + ((size_t)(SL_LA + 2 * li) * B + p) * n;
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(1024) k_chunk_scan(fe_t* __restrict__ chunk_pr
 }
 __global__ void __launch_bounds__(128)
 k_z_write(fe_t* __restrict__ P, const fe_t* __restrict__ ratio, const fe_t* __restrict__ chunk_prefix, uint32_t n, uint32_t B, uint32_t nz_total,
-          uint64_t seed, uint32_t p_base) {
+          const BlindKey seed, uint32_t p_base) {
     const uint32_t nch = n / CH;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nz_total * nch) return;
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(256) k_perm_chain(fe_t* __restrict__ P, uint32
     fe_t* z = P + ((size_t)(SL_PZ + set) * B + p) * n + row;
     stv(z, Fr::mul(ldv(z), last));
 }
-__global__ void __launch_bounds__(256) k_random_poly(fe_t* __restrict__ P, uint32_t n, uint32_t B, uint64_t seed, uint32_t p_base) {
+__global__ void __launch_bounds__(256) k_random_poly(fe_t* __restrict__ P, uint32_t n, uint32_t B, const BlindKey seed, uint32_t p_base) {
     const uint32_t p = blockIdx.y, row = blockIdx.x * 256 + threadIdx.x;
     if (row >= n) return;
     stv(P + ((size_t)SL_RAND * B + p) * n + row, blind_value(seed, p_base + p, ST_RANDOM_POLY, row));
@@ -694,10 +696,14 @@ static void pk_release(b2r_pk* pk) {
 
 extern "C" {
 
-int32_t b2r_rsa_keygen(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g, const b2r_bases* g_lagrange, b2r_pk** out) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_rsa_keygen(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g, const b2r_bases* g_lagrange, b2r_pk** out) try {
+    B2R_ENTER(ctx);
     if (!prog || !g || !g_lagrange || !out) return fail(ctx, B2R_ERR_INVALID, "rsa_keygen: null argument");
     *out = nullptr;
+    // the two base sets must be the SRS of THIS circuit size: g needs >= 2^k points (commit of degree < 2^k polynomials),
+    // g_lagrange exactly 2^k (a Lagrange basis of another domain commits to something else without any error)
+    if (bases_count(g) < ((size_t)1 << prog->k)) return fail(ctx, B2R_ERR_INVALID, "rsa_keygen: g holds fewer than 2^k points");
+    if (bases_count(g_lagrange) != ((size_t)1 << prog->k)) return fail(ctx, B2R_ERR_INVALID, "rsa_keygen: g_lagrange must hold exactly 2^k points");
     b2r_pk* pk = new b2r_pk();
     pk->prog = prog;
     pk->g = g;
@@ -836,14 +842,15 @@ int32_t b2r_rsa_keygen(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases* g, c
     return 0;
 #undef KG_CUDA
 #undef KG_TRY
-}
+} B2R_ABI_CATCH(ctx)
 
-int32_t b2r_pk_free(b2r_ctx* ctx, b2r_pk* pk) {
+int32_t b2r_pk_free(b2r_ctx* ctx, b2r_pk* pk) try {
+    B2R_ENTER(ctx);
     if (!ctx || !pk) return B2R_ERR_INVALID;
     cudaStreamSynchronize(ctx->stream);
     pk_release(pk);
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 int32_t b2r_pk_info(const b2r_pk* pk, uint32_t* k, uint32_t* ext_k, uint32_t* num_fixed, uint32_t* num_sigma, uint64_t* proof_bytes) {
     if (!pk) return B2R_ERR_INVALID;
@@ -852,6 +859,21 @@ int32_t b2r_pk_info(const b2r_pk* pk, uint32_t* k, uint32_t* ext_k, uint32_t* nu
     if (num_fixed) *num_fixed = NFIXED;
     if (num_sigma) *num_sigma = NPERM;
     if (proof_bytes) *proof_bytes = 32 * (NADV + 2 * NLOOK + NSETS + NLOOK + 1 + QD + NPOINTS + NEVAL);
+    return 0;
+}
+
+int32_t b2r_pk_set_transcript_repr(b2r_pk* pk, const b2r_fr* transcript_repr) {
+    if (!pk || !transcript_repr) return B2R_ERR_INVALID;
+    // must be a reduced Montgomery representation (what a Rust Fr holds in memory)
+    fe_t v;
+    for (int i = 0; i < 4; i++) {
+        v.l[2 * i] = (uint32_t)transcript_repr->l[i];
+        v.l[2 * i + 1] = (uint32_t)(transcript_repr->l[i] >> 32);
+    }
+    uint32_t m[8], t[8];
+    for (int i = 0; i < 8; i++) m[i] = FrP::MOD(i);
+    if (!sub8(t, v.l, m)) return B2R_ERR_INVALID;  // >= r
+    pk->transcript_repr = v;
     return 0;
 }
 
@@ -939,7 +961,7 @@ static void parallel_for_proofs(uint32_t count, F body) {
 
 // one group of at most `B` proofs, inputs already on the device
 static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, const uint64_t* d_s, const uint64_t* d_h, uint32_t B,
-                           uint64_t seed, uint32_t p_base, uint8_t* proofs_host, uint8_t* status_host, size_t proof_bytes) {
+                           const BlindKey& seed, uint32_t p_base, uint8_t* proofs_host, uint8_t* status_host, size_t proof_bytes) {
     const uint32_t n = pk->n, ext_n = pk->ext_n, u = pk->u, k = pk->k, T = pk->T;
     const uint32_t QB = std::min<uint32_t>(B, 16);
     const uint32_t nch = n / CH;
@@ -1188,36 +1210,28 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
 extern "C" {
 
 static int32_t prove_all(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, const uint64_t* d_s, const uint64_t* d_h, size_t batch,
-                         uint64_t seed, uint8_t* proofs, uint8_t* status) {
+                         const BlindKey& bkey, uint8_t* proofs, uint8_t* status) {
     uint64_t proof_bytes = 0;
     b2r_pk_info(pk, nullptr, nullptr, nullptr, nullptr, &proof_bytes);
     const size_t nl = pk->prog->num_limbs;
     // group size bounded by a memory budget (about 230 MiB of arena per proof at k = 17)
     const size_t per_proof = ((size_t)NSLOT + QD + 3 * NZ + 2 * NPOINTS) * pk->n * 32 + 4096;
     size_t G = std::max<size_t>(1, std::min<size_t>(64, ((size_t)48 << 30) / per_proof));
+    if (const char* ov = getenv("B2R_PROVE_GROUP")) G = std::max<size_t>(1, std::min<size_t>(G, (size_t)atoi(ov)));  // tests: force several groups
     for (size_t p0 = 0; p0 < batch; p0 += G) {
         const uint32_t g = (uint32_t)std::min(G, batch - p0);
-        B2R_TRY(prove_group(ctx, pk, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * pk->prog->aux_words, g, seed, (uint32_t)p0, proofs + p0 * proof_bytes, status + p0,
+        B2R_TRY(prove_group(ctx, pk, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * pk->prog->aux_words, g, bkey, (uint32_t)p0, proofs + p0 * proof_bytes, status + p0,
                             (size_t)proof_bytes));
     }
     return 0;
 }
 
-int32_t b2r_rsa_prove_batch_dev(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
-                                const uint64_t* hash_limbs_dev, size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status) {
-    if (!ctx) return B2R_ERR_INVALID;
-    if (!pk || !n_limbs_dev || !sig_limbs_dev || !hash_limbs_dev || !proofs || !status) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: null pointer");
-    if (seed == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: seed must be non-zero (blinding rows)");
-    if (batch == 0) return 0;
-    return prove_all(ctx, pk, n_limbs_dev, sig_limbs_dev, hash_limbs_dev, batch, seed, proofs, status);
-}
-
-int32_t b2r_rsa_prove_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs, const uint64_t* hash_limbs,
-                            size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status) {
-    if (!ctx) return B2R_ERR_INVALID;
+static int32_t prove_entry(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs, const uint64_t* hash_limbs,
+                           size_t batch, const BlindKey& bkey, bool inputs_on_device, uint8_t* proofs, uint8_t* status) {
     if (!pk || !n_limbs || !sig_limbs || !hash_limbs || !proofs || !status) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: null pointer");
-    if (seed == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: seed must be non-zero (blinding rows)");
     if (batch == 0) return 0;
+    if (batch > 0xffffffffull) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: batch too large");
+    if (inputs_on_device) return prove_all(ctx, pk, n_limbs, sig_limbs, hash_limbs, batch, bkey, proofs, status);
     const size_t nl = pk->prog->num_limbs;
     uint64_t* d_in = nullptr;
     const size_t aw = pk->prog->aux_words;
@@ -1226,7 +1240,40 @@ int32_t b2r_rsa_prove_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_li
     B2R_CUDA(ctx, cudaMemcpyAsync(d_n, n_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
     B2R_CUDA(ctx, cudaMemcpyAsync(d_s, sig_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
     B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * aw * 8, cudaMemcpyHostToDevice, ctx->stream));
-    return prove_all(ctx, pk, d_n, d_s, d_h, batch, seed, proofs, status);
+    return prove_all(ctx, pk, d_n, d_s, d_h, batch, bkey, proofs, status);
 }
+
+// the 64-bit-seed entry points draw a fresh nonce from the context for every call, so that reusing a seed never
+// repeats a blinding stream (two witnesses under identical blinds would leak their difference)
+int32_t b2r_rsa_prove_batch_dev(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
+                                const uint64_t* hash_limbs_dev, size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status) try {
+    B2R_ENTER(ctx);
+    if (seed == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: seed must be non-zero (blinding rows)");
+    return prove_entry(ctx, pk, n_limbs_dev, sig_limbs_dev, hash_limbs_dev, batch, blind_key_from_seed64(seed, ctx->prove_calls++), true, proofs, status);
+} B2R_ABI_CATCH(ctx)
+
+int32_t b2r_rsa_prove_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs, const uint64_t* hash_limbs,
+                            size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status) try {
+    B2R_ENTER(ctx);
+    if (seed == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: seed must be non-zero (blinding rows)");
+    return prove_entry(ctx, pk, n_limbs, sig_limbs, hash_limbs, batch, blind_key_from_seed64(seed, ctx->prove_calls++), false, proofs, status);
+} B2R_ABI_CATCH(ctx)
+
+int32_t b2r_rsa_prove_batch_ex(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs, const uint64_t* hash_limbs,
+                               size_t batch, const uint8_t seed32[32], uint64_t nonce, uint32_t flags, uint8_t* proofs, uint8_t* status) try {
+    B2R_ENTER(ctx);
+    if (!seed32) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: null seed");
+    if (flags & ~(uint32_t)(B2R_PROVE_INPUTS_ON_DEVICE | B2R_PROVE_SEED64)) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: unknown flag");
+    BlindKey bkey;
+    if (flags & B2R_PROVE_SEED64) {
+        uint64_t s64 = 0;
+        for (int i = 0; i < 8; i++) s64 |= (uint64_t)seed32[i] << (8 * i);
+        if (s64 == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_prove: seed must be non-zero (blinding rows)");
+        bkey = blind_key_from_seed64(s64, nonce);
+    } else {
+        bkey = blind_key_from_bytes(seed32, nonce);
+    }
+    return prove_entry(ctx, pk, n_limbs, sig_limbs, hash_limbs, batch, bkey, (flags & B2R_PROVE_INPUTS_ON_DEVICE) != 0, proofs, status);
+} B2R_ABI_CATCH(ctx)
 
 }  // extern "C"

@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(1024) k_witness_eval(const WitnessArgs A) {
 
 __global__ void __launch_bounds__(256)
 k_witness_emit(const int32_t* __restrict__ cellmap, const fe_t* __restrict__ values, uint32_t num_values, uint32_t k,
-               uint32_t usable_rows, uint64_t blind_seed, uint32_t p_base, fe_t* __restrict__ advice, size_t p_stride,
+               uint32_t usable_rows, const BlindKey bkey, uint32_t p_base, fe_t* __restrict__ advice, size_t p_stride,
                size_t col_stride) {
     const uint32_t n = 1u << k;
     uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -510,7 +510,7 @@ k_witness_emit(const int32_t* __restrict__ cellmap, const fe_t* __restrict__ val
     if (row >= n) return;
     fe_t v;
     if (row >= usable_rows) {
-        v = blind_seed ? blind_value(blind_seed, p_base + p, ST_ADVICE + col, row) : Fr::zero();
+        v = bkey.on ? blind_value(bkey, p_base + p, ST_ADVICE + col, row) : Fr::zero();
     } else {
         int32_t id = cellmap[(size_t)col * n + row];
         v = id < 0 ? Fr::zero() : ldv(values + (size_t)p * num_values + id);
@@ -657,8 +657,8 @@ static int32_t build_program(b2r_ctx* ctx, uint32_t bits_len, uint32_t k, uint32
 
 extern "C" {
 
-int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_le, size_t e_len, uint32_t k, b2r_prog** out) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_le, size_t e_len, uint32_t k, b2r_prog** out) try {
+    B2R_ENTER(ctx);
     if (!out || !e_le || e_len == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: null argument");
     *out = nullptr;
     if (bits_len < 512 || bits_len > 4096 || bits_len % 64) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: bits_len must be a multiple of 64 in [512, 4096]");
@@ -668,30 +668,31 @@ int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_
     if (!e_nonzero) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build: exponent is zero");
     std::vector<uint8_t> e(e_le, e_le + e_len);
     return build_program(ctx, bits_len, k, 4, [&](RegionCtx& rc) { return record_rsa_pkcs1v15(rc, bits_len, e); }, out);
-}
+} B2R_ABI_CATCH(ctx)
 
-int32_t b2r_rsa_program_build_var(b2r_ctx* ctx, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_rsa_program_build_var(b2r_ctx* ctx, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out) try {
+    B2R_ENTER(ctx);
     if (!out) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build_var: null argument");
     if (exp_limb_bits == 0 || exp_limb_bits > 64) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build_var: exp_limb_bits must be in [1, 64]");
     return build_program(ctx, bits_len, k, 5, [&](RegionCtx& rc) { return record_rsa_pkcs1v15_var(rc, bits_len, exp_limb_bits); }, out);
-}
+} B2R_ABI_CATCH(ctx)
 
-int32_t b2r_bigint_program_build(b2r_ctx* ctx, uint32_t op, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out) {
-    if (!ctx) return B2R_ERR_INVALID;
+int32_t b2r_bigint_program_build(b2r_ctx* ctx, uint32_t op, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out) try {
+    B2R_ENTER(ctx);
     if (!out) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: null argument");
     if (op < BT_REFRESH || op > BT_SQUARE_MOD) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: unknown operation");
     if (exp_limb_bits == 0 || exp_limb_bits > 64) return fail(ctx, B2R_ERR_INVALID, "bigint_program_build: exp_limb_bits must be in [1, 64]");
     // inputs a | b | n | e: the third array carries n and e (num_limbs + 1 words per instance)
     return build_program(ctx, bits_len, k, bits_len / 64 + 1, [&](RegionCtx& rc) { return record_bigint_op(rc, op, bits_len, exp_limb_bits, nullptr); }, out);
-}
+} B2R_ABI_CATCH(ctx)
 
-int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog* prog) {
+int32_t b2r_prog_free(b2r_ctx* ctx, b2r_prog* prog) try {
+    B2R_ENTER(ctx);
     if (!ctx || !prog) return B2R_ERR_INVALID;
     cudaStreamSynchronize(ctx->stream);
     prog_release(prog);
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 int32_t b2r_prog_num_limbs(const b2r_prog* prog) { return prog ? (int32_t)prog->num_limbs : B2R_ERR_INVALID; }
 int32_t b2r_prog_aux_words(const b2r_prog* prog) { return prog ? (int32_t)prog->aux_words : B2R_ERR_INVALID; }
@@ -709,7 +710,7 @@ int32_t b2r_prog_info(const b2r_prog* prog, uint64_t* rows_used, uint64_t* num_v
 namespace b2r {
 // advice cell (p, col, row) is written to advice_dev[p * p_stride + col * col_stride + row]
 int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
-                    const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev,
+                    const uint64_t* hash_limbs_dev, size_t batch, const BlindKey& bkey, b2r_fr* advice_dev,
                     uint8_t* is_valid_dev, size_t p_base, size_t p_stride, size_t col_stride) {
     if (!ctx) return B2R_ERR_INVALID;
     if (!prog || !n_limbs_dev || !sig_limbs_dev || !hash_limbs_dev || !advice_dev || !is_valid_dev)
@@ -748,7 +749,7 @@ int32_t witness_run(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_
         B2R_LAUNCH_CHECK(ctx);
         dim3 grid((n + 255) / 256, NUM_ADVICE, (unsigned)g);
         KTimer kt_emit(ctx, "witness_emit", (double)g);
-        k_witness_emit<<<grid, 256, 0, ctx->stream>>>(prog->d_cellmap, values, prog->num_values, prog->k, n - BLINDING_ROWS, blind_seed,
+        k_witness_emit<<<grid, 256, 0, ctx->stream>>>(prog->d_cellmap, values, prog->num_values, prog->k, n - BLINDING_ROWS, bkey,
                                                       (uint32_t)(p_base + p0), (fe_t*)advice_dev + p0 * p_stride, p_stride, col_stride);
         B2R_LAUNCH_CHECK(ctx);
     }
@@ -760,15 +761,16 @@ extern "C" {
 
 int32_t b2r_rsa_witness_batch_dev(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
                                   const uint64_t* hash_limbs_dev, size_t batch, uint64_t blind_seed, b2r_fr* advice_dev,
-                                  uint8_t* is_valid_dev) {
+                                  uint8_t* is_valid_dev) try {
+    B2R_ENTER(ctx);
     if (!prog) return ctx ? fail(ctx, B2R_ERR_INVALID, "rsa_witness: null pointer") : B2R_ERR_INVALID;
     const size_t n = (size_t)1 << prog->k;
-    return witness_run(ctx, prog, n_limbs_dev, sig_limbs_dev, hash_limbs_dev, batch, blind_seed, advice_dev, is_valid_dev, 0, NUM_ADVICE * n, n);
-}
+    return witness_run(ctx, prog, n_limbs_dev, sig_limbs_dev, hash_limbs_dev, batch, blind_key_from_seed64(blind_seed, 0), advice_dev, is_valid_dev, 0, NUM_ADVICE * n, n);
+} B2R_ABI_CATCH(ctx)
 
 int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs, const uint64_t* sig_limbs,
-                              const uint64_t* hash_limbs, size_t batch, uint64_t blind_seed, b2r_fr* advice, uint8_t* is_valid) {
-    if (!ctx) return B2R_ERR_INVALID;
+                              const uint64_t* hash_limbs, size_t batch, uint64_t blind_seed, b2r_fr* advice, uint8_t* is_valid) try {
+    B2R_ENTER(ctx);
     if (!prog || !n_limbs || !sig_limbs || !hash_limbs || !advice || !is_valid) return fail(ctx, B2R_ERR_INVALID, "rsa_witness: null pointer");
     if (batch == 0) return 0;
     const size_t n = (size_t)1 << prog->k, nl = prog->num_limbs;
@@ -790,13 +792,13 @@ int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t
     B2R_CUDA(ctx, cudaMemcpyAsync(d_h, hash_limbs, batch * aw * 8, cudaMemcpyHostToDevice, ctx->stream));
     for (size_t p0 = 0; p0 < batch; p0 += G) {
         size_t g = std::min(G, batch - p0);
-        B2R_TRY(witness_run(ctx, prog, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * aw, g, blind_seed, (b2r_fr*)d_adv, d_valid + p0, p0, NUM_ADVICE * n, n));
+        B2R_TRY(witness_run(ctx, prog, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * aw, g, blind_key_from_seed64(blind_seed, 0), (b2r_fr*)d_adv, d_valid + p0, p0, NUM_ADVICE * n, n));
         B2R_CUDA(ctx, cudaMemcpyAsync((char*)advice + p0 * per_adv, d_adv, g * per_adv, cudaMemcpyDeviceToHost, ctx->stream));
         B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     B2R_CUDA(ctx, cudaMemcpyAsync(is_valid, d_valid, batch, cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
-}
+} B2R_ABI_CATCH(ctx)
 
 }  // extern "C"

@@ -168,8 +168,9 @@ int32_t b2r_bigint_program_build(b2r_ctx* ctx, uint32_t op, uint32_t bits_len, u
 /* n_limbs, sig_limbs: batch x (bits_len/64) little-endian 64-bit limbs; hash_limbs:
  * batch x 4.  advice: batch x 5 x 2^k Fr, column-major per instance (HOST pointer);
  * is_valid: batch bytes (the value of the circuit's final is_valid cell).
- * blind_seed != 0 fills the last 6 rows of every column with a seeded stream (the rows
- * halo2's create_proof fills from its RNG); 0 leaves them zero. */
+ * blind_seed != 0 fills the last 6 rows of every column with the seeded blinding stream (the rows
+ * halo2's create_proof fills from its RNG; nonce 0, i.e. reproducible: these entry points expose the
+ * advice table, the complete prover is b2r_rsa_prove_batch*); 0 leaves them zero. */
 int32_t b2r_rsa_witness_batch(b2r_ctx* ctx, const b2r_prog* prog, const uint64_t* n_limbs,
                               const uint64_t* sig_limbs, const uint64_t* hash_limbs, size_t batch,
                               uint64_t blind_seed, b2r_fr* advice, uint8_t* is_valid);
@@ -209,18 +210,39 @@ int32_t b2r_pk_free(b2r_ctx* ctx, b2r_pk* pk);
 int32_t b2r_pk_info(const b2r_pk* pk, uint32_t* k, uint32_t* ext_k, uint32_t* num_fixed, uint32_t* num_sigma, uint64_t* proof_bytes);
 /* verifying key: num_fixed fixed-column commitments, num_sigma permutation commitments, vk transcript scalar */
 int32_t b2r_pk_export_vk(const b2r_pk* pk, b2r_g1_affine* fixed_commitments, b2r_g1_affine* sigma_commitments, b2r_fr* transcript_repr);
+/* halo2's VerifyingKey::transcript_repr is Blake2b("Halo2-Verify-Key") over the Rust Debug string of vk.pinned(),
+ * which only the Rust crate can produce; b2r_rsa_keygen installs a stand-in (a hash of k and the vk commitments) that
+ * only this repo's oracle verifier shares.  A Rust caller MUST pass the real value (vk.transcript_repr, private in
+ * halo2_proofs: the shim in INTEGRATION.md section 3 obtains it by absorbing the vk into a probe transcript) before
+ * proving, or stock verify_proof derives different challenges and rejects every proof.  Reduced Montgomery limbs. */
+int32_t b2r_pk_set_transcript_repr(b2r_pk* pk, const b2r_fr* transcript_repr);
 /* Replaces create_proof::<KZGCommitmentScheme<Bn256>, ProverGWC<_>, Challenge255<_>, _, Blake2bWrite<..>, _>
  * (reference benches/bench.rs:319-331) for `batch` independent instances: HOST inputs as in
  * b2r_rsa_witness_batch, HOST outputs: proofs = batch x proof_bytes (b2r_pk_info), status = batch bytes
  * (1 = proof of a valid signature; 0 = the witness does not satisfy the circuit, the proof will not verify;
  * 0xFF = the reference's synthesize would have panicked; 0xFE = a range-checked cell is out of range).
- * `seed` (non-zero) keys the blinding stream that stands in for the reference's OsRng. */
+ * `seed` (non-zero) keys the blinding stream that stands in for the reference's OsRng: ChaCha20 blocks reduced mod r
+ * (DESIGN.md section 4a).  These two entry points expand the 64-bit seed into the 256-bit ChaCha key (64 bits of
+ * entropy: tests and benchmarks) and take a fresh nonce from the context on every call, so the same seed never yields
+ * the same blinds twice; b2r_rsa_prove_batch_ex takes the full key and an explicit nonce. */
 int32_t b2r_rsa_prove_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs,
                             const uint64_t* hash_limbs, size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status);
 /* same with the instance inputs already resident in HBM (DEVICE pointers); proofs / status are HOST buffers: the proof
  * bytes are assembled by the per-proof transcripts on the host. */
 int32_t b2r_rsa_prove_batch_dev(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs_dev, const uint64_t* sig_limbs_dev,
                                 const uint64_t* hash_limbs_dev, size_t batch, uint64_t seed, uint8_t* proofs, uint8_t* status);
+
+/* The same with caller-owned randomness: seed32 = 32 bytes from the host's CSPRNG (the ChaCha20 key; what OsRng is to
+ * the reference), nonce = any value the caller never repeats under one key (a proof-batch counter).  (key, nonce,
+ * instance index) determine every blinding value, so a call is reproducible - the parity tests rely on that - and a
+ * caller who repeats a (key, nonce) pair for different witnesses gives up zero knowledge for them.
+ * flags: B2R_PROVE_INPUTS_ON_DEVICE = the three input arrays are device pointers; B2R_PROVE_SEED64 = only the first 8
+ * bytes of seed32 are used, expanded as the 64-bit-seed entry points do (test vectors). */
+#define B2R_PROVE_INPUTS_ON_DEVICE 1u
+#define B2R_PROVE_SEED64 2u
+int32_t b2r_rsa_prove_batch_ex(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs,
+                               const uint64_t* hash_limbs, size_t batch, const uint8_t seed32[32], uint64_t nonce,
+                               uint32_t flags, uint8_t* proofs, uint8_t* status);
 
 #ifdef __cplusplus
 }

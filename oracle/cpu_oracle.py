@@ -92,6 +92,15 @@ def g1_scalar_muls(scalars: np.ndarray, threads: int = 0) -> np.ndarray:
     return out
 
 
+def fr_sub_arrays(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """elementwise a - b over Fr on Montgomery arrays"""
+    a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    assert a.shape == b.shape
+    lib().orc_fr_sub_array(_p(a), _p(b), C.c_size_t(a.shape[0]))
+    return a
+
+
 # ---- hot path (a): witness synthesis oracle (oracle/rsa_witness.c) ---------------------------
 class RsaTable:
     """One synthesized circuit table: the oracle's Circuit::synthesize for the bench circuit

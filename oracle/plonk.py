@@ -80,27 +80,67 @@ def g1_np_to_point(a):
     return None if x == 0 and y == 0 else (x, y)
 
 
-# ---- seeded randomness (the stand-in for OsRng on both sides) ----------------------------------
-def _splitmix64(x):
-    x = (x + 0x9E3779B97F4A7C15) & MASK64
-    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & MASK64
-    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & MASK64
-    return x ^ (x >> 31)
+# ---- keyed randomness (the stand-in for OsRng on both sides) -----------------------------------
+# Blinding stream v2 (product: csrc/devutil.cuh): one ChaCha20 block (RFC 7539 block function) per blinded cell,
+# key = 32 seed bytes, word 12 = row | stream << 24, word 13 = proof index, words 14-15 = call nonce; the 64 output
+# bytes are a little-endian integer reduced mod r (halo2curves Fr::from_bytes_wide, i.e. what Fr::random does).
+_SEED64_PAD = b"b2rsa-blind-seed64-v2"
 
 
-_RINV = pow(O.MONT_R, -1, R)
+def blind_key(seed):
+    """seed: 32 bytes (the ChaCha20 key) or an int (64-bit test seed, expanded with a fixed pad) -> 8 key words"""
+    if isinstance(seed, int):
+        kb = (seed & MASK64).to_bytes(8, "little") + _SEED64_PAD + bytes(24 - len(_SEED64_PAD))
+    else:
+        kb = bytes(seed)
+    assert len(kb) == 32
+    return struct.unpack("<8I", kb)
 
 
-def blind_fe(seed, proof, stream, row):
-    """the product's blind_value(): raw 254-bit limbs taken as a Montgomery representation"""
-    base = _splitmix64(seed ^ _splitmix64(((proof << 40) | (stream << 28) | row) & MASK64))
-    x = 0
-    for j in range(4):
-        x |= _splitmix64((base + j) & MASK64) << (64 * j)
-    x &= (1 << 254) - 1
-    if x >= R:
-        x -= R
-    return x * _RINV % R
+def _chacha20_blocks(key_words, w12, w13, nonce):
+    """vectorised over w12 (uint32 array) -> uint32[len, 16] output blocks"""
+    w12 = np.asarray(w12, dtype=np.uint32)
+    m = w12.shape[0]
+    init = np.empty((16, m), dtype=np.uint32)
+    const = (0x61707865, 0x3320646E, 0x79622D32, 0x6B206574)
+    for i in range(4):
+        init[i] = const[i]
+    for i in range(8):
+        init[4 + i] = key_words[i]
+    init[12] = w12
+    init[13] = w13 & 0xFFFFFFFF
+    init[14] = nonce & 0xFFFFFFFF
+    init[15] = (nonce >> 32) & 0xFFFFFFFF
+    x = init.copy()
+
+    def rotl(v, n):
+        return (v << np.uint32(n)) | (v >> np.uint32(32 - n))
+
+    def qr(a, b, c, d):
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16)
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12)
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8)
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7)
+
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+        x += init
+    return np.ascontiguousarray(x.T)
+
+
+def blind_fes(seed, proof, stream, rows, nonce=0):
+    """canonical blinding values of (proof, stream) at the given rows"""
+    rows = np.asarray(list(rows), dtype=np.uint32)
+    if rows.size == 0:
+        return []
+    blocks = _chacha20_blocks(blind_key(seed), rows | np.uint32(stream << 24), proof, nonce).astype("<u4").tobytes()
+    return [int.from_bytes(blocks[64 * i:64 * i + 64], "little") % R for i in range(rows.size)]
+
+
+def blind_fe(seed, proof, stream, row, nonce=0):
+    return blind_fes(seed, proof, stream, [row], nonce)[0]
 
 
 # ---- domain ---------------------------------------------------------------------------------------
@@ -284,8 +324,9 @@ def build_permutation(n, copies):
     return mapping
 
 
-def keygen(layout, srs):
-    """keygen_vk + keygen_pk"""
+def keygen_arrays(layout, srs, threads=0):
+    """keygen_vk + keygen_pk with every polynomial kept as a uint64[., 4] Montgomery array (the form the C prover
+    oracle/plonk_prover.c consumes; Python integer lists of the 2^(k+2) cosets would not fit comfortably at k = 18)"""
     k = layout["k"]
     dom = Domain(k)
     n, u = dom.n, dom.n - (BF + 1)
@@ -304,21 +345,21 @@ def keygen(layout, srs):
     fixed.append([int(x) for x in rng[0]])   # s_composition (complex selector -> fixed column)
     fixed.append([int(x) for x in rng[2]])   # s_overflow
     assert len(fixed) == NUM_FIXED
-    pk = {"k": k, "dom": dom, "table_len": len(t_tag), "fixed_values": fixed}
-    pk["fixed_polys"] = [dom.lagrange_to_coeff(v) for v in fixed]
-    pk["fixed_cosets"] = [dom.coeff_to_extended(p) for p in pk["fixed_polys"]]
-    pk["fixed_commitments"] = [srs.commit_lagrange(v) for v in fixed]
+    ka = {"k": k, "dom": dom, "table_len": len(t_tag)}
+    ka["fixed_values"] = np.stack([ints_to_np(v) for v in fixed])
     mapping = build_permutation(n, layout["copies"])
     omega_pows, acc = [], 1
     for _ in range(n):
         omega_pows.append(acc)
         acc = acc * dom.omega % R
     delta_pows = [pow(O.DELTA, j, R) for j in range(len(PERM_COLUMNS))]
-    sig = [[delta_pows[mapping[c][r][0]] * omega_pows[mapping[c][r][1]] % R for r in range(n)] for c in range(len(PERM_COLUMNS))]
-    pk["sigma_values"] = sig
-    pk["sigma_polys"] = [dom.lagrange_to_coeff(v) for v in sig]
-    pk["sigma_cosets"] = [dom.coeff_to_extended(p) for p in pk["sigma_polys"]]
-    pk["sigma_commitments"] = [srs.commit_lagrange(v) for v in sig]
+    ka["sigma_values"] = np.stack([ints_to_np([delta_pows[mc] * omega_pows[mr] % R for mc, mr in mapping[c]]) for c in range(len(PERM_COLUMNS))])
+    for name in ("fixed", "sigma"):
+        vals = ka[name + "_values"]
+        polys = np.stack([CO.lagrange_to_coeff(v, k, threads) for v in vals])
+        ka[name + "_polys"] = polys
+        ka[name + "_cosets"] = np.stack([CO.coeff_to_extended(p, k, dom.ext_k, threads) for p in polys])
+        ka[name + "_commitments"] = [g1_np_to_point(CO.best_multiexp(v, srs.g_lagrange, threads)) for v in vals]
     l0 = [0] * n
     l0[0] = 1
     lblind = [0] * n
@@ -326,16 +367,65 @@ def keygen(layout, srs):
         lblind[i] = 1
     llast = [0] * n
     llast[n - BF - 1] = 1
-    pk["l0"] = dom.coeff_to_extended(dom.lagrange_to_coeff(l0))
-    lb = dom.coeff_to_extended(dom.lagrange_to_coeff(lblind))
-    pk["l_last"] = dom.coeff_to_extended(dom.lagrange_to_coeff(llast))
-    pk["l_active"] = [(1 - a - b) % R for a, b in zip(pk["l_last"], lb)]
+    ext = lambda v: CO.coeff_to_extended(CO.lagrange_to_coeff(ints_to_np(v), k, threads), k, dom.ext_k, threads)
+    ka["l0"], ka["l_last"] = ext(l0), ext(llast)
+    one_minus = ints_to_np([1] * dom.ext_n)
+    ka["l_active"] = CO.fr_sub_arrays(CO.fr_sub_arrays(one_minus, ka["l_last"]), ext(lblind))
     h = hashlib.blake2b(digest_size=64, person=b"Halo2-Verify-Key")
     h.update(struct.pack("<I", k))
-    for P in pk["fixed_commitments"] + pk["sigma_commitments"]:
+    for P in ka["fixed_commitments"] + ka["sigma_commitments"]:
         h.update(compress_point(P))
-    pk["transcript_repr"] = int.from_bytes(h.digest(), "little") % R
+    ka["transcript_repr"] = int.from_bytes(h.digest(), "little") % R
+    return ka
+
+
+def keygen(layout, srs):
+    """keygen_vk + keygen_pk as Python integer lists (what create_proof / verify_proof below work on)"""
+    ka = keygen_arrays(layout, srs)
+    pk = {"k": ka["k"], "dom": ka["dom"], "table_len": ka["table_len"], "transcript_repr": ka["transcript_repr"],
+          "fixed_commitments": ka["fixed_commitments"], "sigma_commitments": ka["sigma_commitments"], "arrays": ka}
+    for name in ("fixed_values", "fixed_polys", "fixed_cosets", "sigma_values", "sigma_polys", "sigma_cosets"):
+        pk[name] = [np_to_ints(a) for a in ka[name]]
+    for name in ("l0", "l_last", "l_active"):
+        pk[name] = np_to_ints(ka[name])
     return pk
+
+
+class _CKey(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("table_len", C.c_uint32)] + [(nm, C.c_void_p) for nm in (
+        "fixed_values", "fixed_polys", "fixed_cosets", "sigma_values", "sigma_polys", "sigma_cosets", "l0", "l_last", "l_active",
+        "g", "g_lagrange")] + [("transcript_repr", C.c_uint64 * 4)]
+
+
+def create_proof_c(ka, srs, advice_np, seed, proof_index=0, nonce=0, threads=0, transcript_repr=None):
+    """oracle/plonk_prover.c: the same create_proof in C (seconds at k = 17 / 18).  ka = keygen_arrays(..),
+    advice_np = uint64[5, n, 4] Montgomery (CO.RsaTable.advice()).  -> (proof bytes, challenges dict)"""
+    key = _CKey()
+    key.k, key.table_len = ka["k"], ka["table_len"]
+    keep = []
+    for nm in ("fixed_values", "fixed_polys", "fixed_cosets", "sigma_values", "sigma_polys", "sigma_cosets", "l0", "l_last", "l_active"):
+        a = np.ascontiguousarray(ka[nm], dtype=np.uint64)
+        keep.append(a)
+        setattr(key, nm, a.ctypes.data)
+    g = np.ascontiguousarray(srs.g, dtype=np.uint64)
+    gl = np.ascontiguousarray(srs.g_lagrange, dtype=np.uint64)
+    key.g, key.g_lagrange = g.ctypes.data, gl.ctypes.data
+    tr = ints_to_np([ka["transcript_repr"] if transcript_repr is None else transcript_repr])[0]
+    for i in range(4):
+        key.transcript_repr[i] = int(tr[i])
+    adv = np.ascontiguousarray(advice_np, dtype=np.uint64)
+    assert adv.shape == (NUM_ADVICE, 1 << ka["k"], 4)
+    kb = struct.pack("<8I", *blind_key(seed))
+    proof = np.zeros(proof_length(), dtype=np.uint8)
+    chal = np.zeros((6, 4), dtype=np.uint64)
+    L = CO.lib()
+    L.orc_plonk_create_proof.restype = C.c_int
+    rc = L.orc_plonk_create_proof(C.byref(key), _ptr(adv), kb, C.c_uint64(nonce), C.c_uint32(proof_index), C.c_int(threads or CO.ncores()),
+                                  _ptr(proof), _ptr(chal))
+    if rc == -1:
+        raise ValueError("lookup input not in table (ConstraintSystemFailure)")
+    assert rc == 0, rc
+    return proof.tobytes(), dict(zip(("theta", "beta", "gamma", "y", "x", "v"), np_to_ints(chal)))
 
 
 # ---- prover --------------------------------------------------------------------------------------------
@@ -387,7 +477,7 @@ def kate_division(coeffs, z):
     return q
 
 
-def create_proof(pk, srs, advice, seed, proof_index=0, trace=None):
+def create_proof(pk, srs, advice, seed, proof_index=0, trace=None, nonce=0):
     """advice: 5 lists of n canonical values whose last BF+1 rows are ignored (re-blinded here).
     Returns the proof bytes.  `trace` (dict) receives intermediate values for stage-by-stage tests."""
     dom = pk["dom"]
@@ -396,7 +486,7 @@ def create_proof(pk, srs, advice, seed, proof_index=0, trace=None):
     tr = Transcript()
     tr.common_scalar(pk["transcript_repr"])
     # (no instance values: the sha-disabled circuit has an empty instance column)
-    adv = [list(col[:u]) + [blind_fe(seed, proof_index, ST_ADVICE + c, r) for r in range(u, n)] for c, col in enumerate(advice)]
+    adv = [list(col[:u]) + blind_fes(seed, proof_index, ST_ADVICE + c, range(u, n), nonce) for c, col in enumerate(advice)]
     adv_polys = [dom.lagrange_to_coeff(v) for v in adv]
     for v in adv:
         tr.write_point(srs.commit_lagrange(v))
@@ -407,8 +497,8 @@ def create_proof(pk, srs, advice, seed, proof_index=0, trace=None):
     for li, (acol, ftag, fsel) in enumerate(LOOKUPS):
         A = [(fx[ftag][i] * theta + fx[fsel][i] * adv[acol][i]) % R for i in range(n)]
         a_p, s_p = permute_expression_pair(A, table, u)
-        a_p += [blind_fe(seed, proof_index, ST_LOOKUP_A + li, r) for r in range(u, n)]
-        s_p += [blind_fe(seed, proof_index, ST_LOOKUP_S + li, r) for r in range(u, n)]
+        a_p += blind_fes(seed, proof_index, ST_LOOKUP_A + li, range(u, n), nonce)
+        s_p += blind_fes(seed, proof_index, ST_LOOKUP_S + li, range(u, n), nonce)
         tr.write_point(srs.commit_lagrange(a_p))
         tr.write_point(srs.commit_lagrange(s_p))
         lk.append({"A": A, "a_p": a_p, "s_p": s_p})
@@ -435,8 +525,7 @@ def create_proof(pk, srs, advice, seed, proof_index=0, trace=None):
         z = [last_z]
         for row in range(1, n):
             z.append(z[-1] * num[row - 1] % R * inv[row - 1] % R)
-        for r in range(n - BF, n):
-            z[r] = blind_fe(seed, proof_index, ST_PERM_Z + ch // CHUNK, r)
+        z[n - BF:] = blind_fes(seed, proof_index, ST_PERM_Z + ch // CHUNK, range(n - BF, n), nonce)
         last_z = z[n - BF - 1]
         perm_z.append(z)
     for z in perm_z:
@@ -448,11 +537,11 @@ def create_proof(pk, srs, advice, seed, proof_index=0, trace=None):
         z = [1]
         for i in range(u):
             z.append(z[-1] * ((d["A"][i] + beta) % R) % R * ((table[i] + gamma) % R) % R * inv[i] % R)
-        z = z[: n - BF] + [blind_fe(seed, proof_index, ST_LOOKUP_Z + li, r) for r in range(n - BF, n)]
+        z = z[: n - BF] + blind_fes(seed, proof_index, ST_LOOKUP_Z + li, range(n - BF, n), nonce)
         d["z"] = z
         tr.write_point(srs.commit_lagrange(z))
     # vanishing argument: random polynomial
-    random_poly = [blind_fe(seed, proof_index, ST_RANDOM_POLY, r) for r in range(n)]
+    random_poly = blind_fes(seed, proof_index, ST_RANDOM_POLY, range(n), nonce)
     tr.write_point(srs.commit(random_poly))
     y = tr.squeeze()
     # quotient on the extended domain

@@ -283,6 +283,7 @@ void orc_g1_scalar_muls(const fe* scalars, g1a* out, size_t n, int nthreads) {
     smul_job j = {scalars, out, n};
     run_parallel(smul_fn, &j, nthreads);
 }
+void orc_fr_sub_array(fe* a, const fe* b, size_t n) { for (size_t i = 0; i < n; i++) a[i] = fe_sub(&FR, &a[i], &b[i]); }
 void orc_fr_mul_array(fe* a, const fe* b, size_t n) { for (size_t i = 0; i < n; i++) a[i] = fe_mul(&FR, &a[i], &b[i]); }
 
 /* bulk conversions for the Python oracle prover: canonical <-> Montgomery, in place */

@@ -128,3 +128,45 @@ def test_msm_uniform_hint_same_result(ctx):
     for j, v in enumerate(vecs):
         assert got[j] == O.g1_mul(O.G1_GEN, sum(s * (i + 1) for i, s in enumerate(v)) % O.R_MOD)
     bs.free()
+
+
+def test_msm_2p20_config5(ctx):
+    """BASELINE configs[4] size (standalone MSM 2^20): bases (i+1) G from the C oracle, (a) uniform seeded scalars and
+    (b) advice-like skew (zeros, bits, bytes, 64-bit limbs, a few full-size values), each against the closed form
+    (sum s_i (i+1)) G AND against the CPU best_multiexp restatement (oracle/poly.c), with and without the uniform hint"""
+    import torch
+    import cpu_oracle as CO
+    import plonk as PL
+    from util import random_fr_np
+    n = 1 << 20
+    bases = CO.g1_multiples(n)
+    bs = ctx.bases_register(bases)
+    uni = random_fr_np(n, 0x5EED)
+    rng = np.random.default_rng(20)
+    sel = rng.integers(0, 10, size=n)
+    skew = uni.copy()
+    skew[sel < 4] = 0
+    one = fr_to_np([1])[0]
+    skew[(sel >= 4) & (sel < 6)] = one
+    small = PL.ints_to_np([int(x) for x in rng.integers(0, 256, size=n)])
+    limb = PL.ints_to_np([int(x) for x in rng.integers(0, 1 << 63, size=n, dtype=np.uint64)])
+    m = (sel >= 6) & (sel < 8)
+    skew[m] = small[m]
+    m = sel == 8
+    skew[m] = limb[m]
+    arr = np.stack([uni, skew])
+    t = torch.from_numpy(arr.view(np.int64)).cuda()
+    outs = []
+    for hint in (False, True):
+        out = torch.zeros(2 * 8, dtype=torch.int64, device="cuda")
+        ctx.msm_batch_dev(bs, t.data_ptr(), 2, n, out.data_ptr(), uniform=hint)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy().view(np.uint64).reshape(2, 8))
+    assert np.array_equal(outs[0], outs[1])
+    got = np_to_g1(outs[0])
+    for j in range(2):
+        vals = PL.np_to_ints(arr[j])
+        want = O.g1_mul(O.G1_GEN, sum(s * (i + 1) for i, s in enumerate(vals)) % O.R_MOD)
+        assert got[j] == want, f"vector {j} vs closed form"
+        assert np.array_equal(CO.best_multiexp(arr[j], bases), outs[0][j]), f"vector {j} vs CPU best_multiexp"
+    bs.free()

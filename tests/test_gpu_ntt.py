@@ -93,3 +93,21 @@ def test_batch_dev_matches_single(ctx):
     got = t.cpu().numpy().view(np.uint64).reshape(batch, 1 << k, 4)
     for b in range(batch):
         assert np.array_equal(got[b], ctx.ntt(a.reshape(batch, 1 << k, 4)[b], w, k))
+
+
+@pytest.mark.parametrize("log_n", [17, 19, 22])
+def test_full_size_full_array_vs_cpu_oracle(ctx, log_n):
+    """BASELINE sizes, every output element: best_fft against the CPU restatement (oracle/poly.c: bit-reversal +
+    radix-2 DIT, a different algorithm from the product's Stockham passes), and at 2^17 -> 2^19 the three
+    EvaluationDomain wrappers create_proof uses"""
+    import cpu_oracle as CO
+    n = 1 << log_n
+    a = random_fr_np(n, 2000 + log_n)
+    w = fr_to_np([O.omega_for(log_n)])[0]
+    assert np.array_equal(ctx.ntt(a, w, log_n), CO.best_fft(a, w, log_n))
+    if log_n == 17:
+        co = ctx.intt(a, log_n)
+        assert np.array_equal(co, CO.lagrange_to_coeff(a, log_n))
+        ext = ctx.coset_ntt(co, log_n, log_n + 2)
+        assert np.array_equal(ext, CO.coeff_to_extended(co, log_n, log_n + 2))
+        assert np.array_equal(ctx.coset_intt(ext, log_n + 2), CO.extended_to_coeff(ext, log_n + 2))

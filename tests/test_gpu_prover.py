@@ -3,8 +3,13 @@ oracle's independent restatement of halo2's keygen_vk / keygen_pk / create_proof
 
   * RSA-512 at k = 14 (a size the Python oracle proves in seconds): verifying key and PROOF BYTES are identical
     for the same seeded randomness - every commitment, challenge, evaluation and opening witness of the proof.
-  * RSA-2048 at k = 17 (BASELINE configs[0]/[1] size): the proofs are accepted by the oracle verifier, a tampered
-    proof and a proof for a wrong signature are rejected.
+  * RSA-2048 at k = 17 (BASELINE configs[0]/[1]) and RSA-4096 at k = 18 (configs[2]): verifying key and ALL 2848
+    PROOF BYTES identical to the C restatement of the same prover (oracle/plonk_prover.c, itself pinned to plonk.py
+    byte for byte at k = 14 by tests/test_oracle_plonk_c.py); the proofs are accepted by the oracle verifier, a
+    tampered proof and a proof for a wrong signature are rejected.
+  * batches that cross the quotient sub-batch (16), a ragged last sub-batch and several proof groups: every proof
+    verified, the proofs at the seams compared byte for byte.
+  * two contexts in one process, calls interleaved.
 """
 import numpy as np
 import pytest
@@ -53,17 +58,150 @@ def test_proof_bytes_match_oracle(small):
     bits, k, pk, srs, opk = small
     seed, batch = 0xB200, 2
     nl, sl, hl = RF.batch(bits, batch, start=1)
-    proofs, status = pk.prove_batch(nl, sl, hl, seed)
+    proofs, status = pk.prove_batch(nl, sl, hl, seed, nonce=3)
     assert status.tolist() == [1] * batch
     for i in range(batch):
         v, adv, rows, bad, msg = CO.rsa_synthesize(bits, k, *RF.instance(bits, 1 + i))
         assert v == 1 and bad == 0
-        want = PL.create_proof(opk, srs, [PL.np_to_ints(adv[c]) for c in range(5)], seed, proof_index=i)
+        want = PL.create_proof(opk, srs, [PL.np_to_ints(adv[c]) for c in range(5)], seed, proof_index=i, nonce=3)
         got = bytes(proofs[i])
         if got != want:   # name the first differing proof element
             first = next(j for j in range(0, len(want), 32) if got[j:j + 32] != want[j:j + 32]) // 32
             raise AssertionError(f"instance {i}: proof element {first} of {len(want) // 32} differs")
         assert PL.verify_proof(opk, srs.s, got)
+
+
+_ORACLE_CACHE = {}
+
+
+def _oracle_key(bits, k):
+    """SRS + keygen of the oracle at (bits, k), cached for the session (tens of seconds at k = 17 / 18)"""
+    if (bits, k) not in _ORACLE_CACHE:
+        srs = PL.Srs(k)
+        _ORACLE_CACHE[(bits, k)] = (srs, PL.keygen_arrays(PL.circuit_layout(bits, k), srs))
+    return _ORACLE_CACHE[(bits, k)]
+
+
+def _assert_same_proof(got, want, what):
+    if got != want:   # name the first differing proof element
+        first = next(j for j in range(0, len(want), 32) if got[j:j + 32] != want[j:j + 32]) // 32
+        raise AssertionError(f"{what}: proof element {first} of {len(want) // 32} differs")
+
+
+@pytest.mark.parametrize("bits,k,count", [(2048, 17, 2), (4096, 18, 1)])
+def test_proof_bytes_match_oracle_at_baseline_sizes(ctx, bits, k, count):
+    """BASELINE configs[1] (RSA-2048, k = 17) and configs[2] (RSA-4096, k = 18): vk commitments and all 2848 proof bytes
+    equal to the oracle prover's for the same key / nonce / instance index"""
+    prog, g, gl, pk = _setup(ctx, bits, k)
+    srs, ka = _oracle_key(bits, k)
+    vk = _vk(pk)
+    assert vk["fixed_commitments"] == ka["fixed_commitments"]
+    assert vk["sigma_commitments"] == ka["sigma_commitments"]
+    assert vk["transcript_repr"] == ka["transcript_repr"]
+    start, seed, nonce = 5, bytes(range(100, 132)), 0x1122334455
+    nl, sl, hl = RF.batch(bits, count, start=start)
+    proofs, status = pk.prove_batch(nl, sl, hl, seed, nonce=nonce)
+    assert status.tolist() == [1] * count
+    for i in range(count):
+        v, adv, rows, bad, msg = CO.rsa_synthesize(bits, k, *RF.instance(bits, start + i))
+        assert v == 1 and bad == 0
+        want, _ = PL.create_proof_c(ka, srs, adv, seed, proof_index=i, nonce=nonce)
+        _assert_same_proof(bytes(proofs[i]), want, f"RSA-{bits} k={k} instance {i}")
+        assert PL.verify_proof(vk, srs.s, want)
+    pk.free(); g.free(); gl.free(); prog.free()
+
+
+@pytest.mark.parametrize("batch,group", [(20, None), (70, None), (9, 4)])
+def test_sub_batches_and_groups(small, monkeypatch, batch, group):
+    """batch 20: quotient sub-batches of 16 + a ragged one of 4 (the per-column coset fallback); batch 70: two proof
+    groups (64 + 6, instance index offset p_base > 0); B2R_PROVE_GROUP=4: three groups.  Every proof must verify; the
+    proofs on both sides of every seam are compared with the oracle prover byte for byte."""
+    bits, k, pk, srs, opk = small
+    if group:
+        monkeypatch.setenv("B2R_PROVE_GROUP", str(group))
+    nl, sl, hl = RF.batch(bits, batch)
+    proofs, status = pk.prove_batch(nl, sl, hl, 0xABCD, nonce=9)
+    assert status.tolist() == [1] * batch
+    for i in range(batch):
+        assert PL.verify_proof(opk, srs.s, bytes(proofs[i])), f"proof {i} of {batch} rejected"
+    assert len({bytes(p) for p in proofs}) == batch
+    seams = {0, batch - 1} | ({15, 16} if batch > 16 else set()) | ({63, 64} if batch > 64 else set()) | ({3, 4, 7, 8} if group else set())
+    for i in sorted(seams):
+        v, adv, rows, bad, msg = CO.rsa_synthesize(bits, k, *RF.instance(bits, i))
+        want, _ = PL.create_proof_c(opk["arrays"], srs, adv, 0xABCD, proof_index=i, nonce=9)
+        _assert_same_proof(bytes(proofs[i]), want, f"batch {batch} instance {i}")
+
+
+def test_two_contexts_interleaved(ctx, small):
+    """a second context in the same process (the header's one-context-per-thread model): programs, SRS, keys and proofs
+    built on both with the calls interleaved give identical results, and the first context still works after the
+    second is destroyed.  (Per-device function attributes / device binding: ctx.hpp DeviceGuard.)"""
+    import b2rsa
+    bits, k, pk, srs, opk = small
+    other = b2rsa.Context(0)
+    prog2 = other.rsa_program(bits, k)
+    g2, gl2 = other.srs_setup(k, fr_to_np([O.srs_secret(k)])[0])
+    nl, sl, hl = RF.batch(bits, 2, start=3)
+    a1, _ = pk.prove_batch(nl[:1], sl[:1], hl[:1], 5, nonce=1)
+    pk2 = other.rsa_keygen(prog2, g2, gl2)
+    b1, _ = pk2.prove_batch(nl[:1], sl[:1], hl[:1], 5, nonce=1)
+    a2, _ = pk.prove_batch(nl[1:], sl[1:], hl[1:], 5, nonce=2)
+    b2, _ = pk2.prove_batch(nl[1:], sl[1:], hl[1:], 5, nonce=2)
+    assert bytes(a1[0]) == bytes(b1[0]) and bytes(a2[0]) == bytes(b2[0])
+    # uniform MSM (binned sort: 80 KB dynamic shared memory attribute) on both contexts
+    from util import random_fr_np
+    import torch
+    n = 1 << k
+    sc = torch.from_numpy(random_fr_np(n, 4).view(np.int64)).cuda()
+    o1 = torch.zeros(8, dtype=torch.int64, device="cuda"); o2 = torch.zeros(8, dtype=torch.int64, device="cuda")
+    gx, glx = ctx.srs_setup(k, fr_to_np([O.srs_secret(k)])[0])
+    ctx.msm_batch_dev(glx, sc.data_ptr(), 1, n, o1.data_ptr(), uniform=True)
+    other.msm_batch_dev(gl2, sc.data_ptr(), 1, n, o2.data_ptr(), uniform=True)
+    ctx.sync(); other.sync()
+    assert torch.equal(o1, o2)
+    pk2.free(); prog2.free(); g2.free(); gl2.free(); gx.free(); glx.free()
+    other.close()
+    a3, st = pk.prove_batch(nl[:1], sl[:1], hl[:1], 5, nonce=1)
+    assert bytes(a3[0]) == bytes(a1[0]) and PL.verify_proof(opk, srs.s, bytes(a3[0]))
+
+
+def test_keygen_rejects_wrong_srs_size(ctx):
+    """a Lagrange basis of another domain must not be accepted silently"""
+    import b2rsa
+    prog = ctx.rsa_program(512, 14)
+    g15, gl15 = ctx.srs_setup(15, fr_to_np([O.srs_secret(15)])[0])
+    g13, gl13 = ctx.srs_setup(13, fr_to_np([O.srs_secret(13)])[0])
+    g14, gl14 = ctx.srs_setup(14, fr_to_np([O.srs_secret(14)])[0])
+    for g, gl in ((g15, gl15), (g14, gl15), (g13, gl14), (g14, gl13)):
+        with pytest.raises(b2rsa.B2RError) as e:
+            ctx.rsa_keygen(prog, g, gl)
+        assert e.value.code == b2rsa.ERR_INVALID
+    pk = ctx.rsa_keygen(prog, g15, gl14)     # a longer g is fine: commit only uses its first 2^k points
+    pk.free()
+    for b in (g13, gl13, g14, gl14, g15, gl15):
+        b.free()
+    prog.free()
+
+
+def test_transcript_repr_override(small):
+    """b2r_pk_set_transcript_repr (what a Rust host passes for the real vk): proofs follow the installed value"""
+    import b2rsa
+    bits, k, pk, srs, opk = small
+    f, s_, t0 = pk.export_vk()
+    nl, sl, hl = RF.batch(bits, 1)
+    new_repr = 0x1234567890ABCDEF1234567890ABCDEF
+    pk.set_transcript_repr(fr_to_np([new_repr])[0])
+    try:
+        assert np_to_fr(pk.export_vk()[2].reshape(1, 4))[0] == new_repr
+        proofs, _ = pk.prove_batch(nl, sl, hl, 3, nonce=4)
+        v, adv, rows, bad, msg = CO.rsa_synthesize(bits, k, *RF.instance(bits, 0))
+        want, _ = PL.create_proof_c(opk["arrays"], srs, adv, 3, proof_index=0, nonce=4, transcript_repr=new_repr)
+        _assert_same_proof(bytes(proofs[0]), want, "transcript_repr override")
+        assert not PL.verify_proof(opk, srs.s, want) and PL.verify_proof(dict(opk, transcript_repr=new_repr), srs.s, want)
+        with pytest.raises(b2rsa.B2RError):
+            pk.set_transcript_repr(np.array([2**64 - 1] * 4, dtype=np.uint64))   # not reduced
+    finally:
+        pk.set_transcript_repr(t0)
 
 
 def test_full_size_proofs_verify(ctx):
@@ -74,7 +212,7 @@ def test_full_size_proofs_verify(ctx):
     nl, sl, hl = RF.batch(bits, 3)
     hl_bad = hl.copy()
     hl_bad[2, 0] ^= np.uint64(1)                      # third instance: wrong message hash
-    proofs, status = pk.prove_batch(nl, sl, hl_bad, seed=7)
+    proofs, status = pk.prove_batch(nl, sl, hl_bad, seed=7, nonce=11)
     assert status.tolist() == [1, 1, 0]
     assert PL.verify_proof(vk, secret, bytes(proofs[0]))
     assert PL.verify_proof(vk, secret, bytes(proofs[1]))
@@ -83,11 +221,17 @@ def test_full_size_proofs_verify(ctx):
     bad = bytearray(proofs[0])
     bad[32 * 40 + 3] ^= 1                                              # one evaluation
     assert not PL.verify_proof(vk, secret, bytes(bad))
-    # same seed, same inputs -> same bytes; other seed -> other blinding -> other proof, still valid
-    again, _ = pk.prove_batch(nl[:1], sl[:1], hl[:1], seed=7)
+    # same key, nonce and inputs -> same bytes; other nonce / other seed -> other blinding -> other proof, still valid
+    again, _ = pk.prove_batch(nl[:1], sl[:1], hl[:1], seed=7, nonce=11)
     assert bytes(again[0]) == bytes(proofs[0])
-    other, _ = pk.prove_batch(nl[:1], sl[:1], hl[:1], seed=8)
-    assert bytes(other[0]) != bytes(proofs[0]) and PL.verify_proof(vk, secret, bytes(other[0]))
+    for kw in ({"seed": 7, "nonce": 12}, {"seed": 8, "nonce": 11}, {"seed": bytes(range(32)), "nonce": 11}):
+        other, _ = pk.prove_batch(nl[:1], sl[:1], hl[:1], **kw)
+        assert bytes(other[0]) != bytes(proofs[0]) and PL.verify_proof(vk, secret, bytes(other[0]))
+    # the plain 64-bit-seed entry point takes a fresh nonce from the context on every call: a reused seed never
+    # repeats a blinding stream
+    a, _ = pk.prove_batch(nl[:1], sl[:1], hl[:1], seed=7)
+    b, _ = pk.prove_batch(nl[:1], sl[:1], hl[:1], seed=7)
+    assert bytes(a[0]) != bytes(b[0]) and PL.verify_proof(vk, secret, bytes(a[0])) and PL.verify_proof(vk, secret, bytes(b[0]))
     pk.free(); g.free(); gl.free(); prog.free()
 
 

@@ -13,6 +13,7 @@ import pytest
 
 import bn254 as O
 import cpu_oracle as CO
+import plonk as PL
 import rsa_fixtures as RF
 
 pytestmark = pytest.mark.gpu
@@ -106,14 +107,6 @@ def test_layout_errors(ctx):
         ctx.rsa_program(2000, 17)  # bits_len % 64 != 0
 
 
-def _splitmix64(x):
-    M = (1 << 64) - 1
-    x = (x + 0x9E3779B97F4A7C15) & M
-    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
-    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M
-    return x ^ (x >> 31)
-
-
 def test_blinding_rows(prog2048):
     seed = 0x1234
     nl, sl, hl = RF.batch(2048, 2)
@@ -125,10 +118,6 @@ def test_blinding_rows(prog2048):
     for p in range(2):
         for col in (0, 4):
             for row in (n - 6, n - 1):
-                base = _splitmix64(seed ^ _splitmix64((p << 40) | (col << 28) | row))
-                words = [_splitmix64((base + j) & ((1 << 64) - 1)) for j in range(4)]
-                x = sum(w << (64 * j) for j, w in enumerate(words)) & ((1 << 254) - 1)
-                if x >= O.R_MOD:
-                    x -= O.R_MOD
+                x = PL.blind_fe(seed, p, col, row) * O.MONT_R % O.R_MOD   # Montgomery limbs in memory
                 got = sum(int(adv[p, col, row, j]) << (64 * j) for j in range(4))
                 assert got == x

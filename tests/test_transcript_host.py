@@ -37,3 +37,20 @@ def test_blake2b_known_answer():
     h.update(b"\x00")
     assert len(h.digest()) == 64
     assert hashlib.blake2b(b"abc").hexdigest().startswith("ba80a53f981c4d0d6a2797b69f12f6e9")   # RFC 7693 appendix A
+
+
+def test_blinding_stream_matches_oracle(tmp_path):
+    """csrc/devutil.cuh blind_value (ChaCha20 block, from_bytes_wide reduction) against oracle/plonk.py blind_fe"""
+    exe = str(tmp_path / "bht")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(HERE, "host", "blind_host_test.cpp")])
+    cases = [(0xB200, 0, 0, 0, 131066), (0xB200, 0, 3, 40, 0), (7, 5, 63, 33, 131071), (0xFFFFFFFFFFFFFFFF, 1 << 40, 1000, 24, 16383),
+             ("key", 9, 2, 8, 77), ("key", (1 << 64) - 1, 0xFFFFFFFF, 44, (1 << 24) - 1)]
+    args = [str(x) for c in cases for x in c]
+    lines = subprocess.check_output([exe] + args, text=True).split()
+    for c, line in zip(cases, lines):
+        seed = bytes(range(32)) if c[0] == "key" else c[0]
+        assert int(line, 16) == P.blind_fe(seed, c[2], c[3], c[4], nonce=c[1]), c
+    # RFC 7539 section 2.3.2 block-function vector through the oracle's vectorised ChaCha20
+    import struct
+    b = P._chacha20_blocks(struct.unpack("<8I", bytes(range(32))), [1], 0x09000000, 0x4a000000)
+    assert [int(x) for x in b[0][:4]] == [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3]
