@@ -11,10 +11,11 @@ Blake2b transcripts on the host between the phases.  Output = 64 proofs of 2848 
   e2e   : the same through the reference-facing C-ABI call b2r_rsa_prove_batch with pinned HOST inputs
           (h2d inside the timed region; the proofs always come back to the host)
   --impl reference : the CPU arm.  The reference is Rust and no cargo/rustc exists in this image, so this
-          times oracle/ (this repo's C restatement of the reference's CPU algorithms: sequential synthesize,
-          best_multiexp, best_fft) on all host cores, for the MSM / FFT / witness work of one proof; the
-          prover glue (quotient evaluation, grand products, evaluations) is NOT included, so the CPU figure
-          is an upper bound on the CPU's proofs/s and the GPU/CPU ratio a lower bound.
+          times oracle/ - this repo's C restatement of the reference's CPU prover - on all host cores for ONE
+          COMPLETE PROOF per step: sequential Circuit::synthesize (oracle/rsa_witness.c) followed by the whole
+          create_proof (oracle/plonk_prover.c: 31 best_multiexp, 45 best_fft, lookups, grand products, quotient,
+          evaluations, GWC multiopen, Blake2b transcript), the same work the GPU arm does per instance.
+  extra : BASELINE configs[4] (standalone MSM 2^20 / NTT 2^22) measured after the timed region with CUDA events.
 
 Multi-GPU (torchrun, one rank per GPU): instances are independent, each rank proves its own 64, then ONE
 NCCL all_gather of the proofs (they carry the commitments; 182 KB per rank); scaling = weak.
@@ -41,13 +42,36 @@ WORKLOAD = ("rsa2048_e65537_k17_batch64_per_gpu: full create_proof per instance 
             "22 coset NTT 2^19 + 1 coset iNTT 2^19, lookups, permutation, quotient, 58 evals, GWC multiopen, Blake2b transcript)")
 MSM_BYTES_PER_TERM = 96  # 32 B scalar + 64 B affine base
 FULL_MSM_PER_PROOF, MSM_WINDOWS = 16, 16  # grand products 7, random poly 1, h pieces 4, GWC witnesses 4; ceil(255 / 16) windows
-# dram__bytes_read.sum + dram__bytes_write.sum of k_accum_entries from the ncu --set full capture summarised in
-# profiles/r01_ncu_final.md: the launch over the 256 quotient-piece columns (full-size scalars) moved 44.52 GB + 2.32 GB
-ACCUM_TRAFFIC_BYTES = 46.8e9
-ACCUM_TRAFFIC_VECTORS = 256
-ACCUM_TRAFFIC_SOURCE = ("ncu --set full, one k_accum_entries launch over 256 x 2^17 full-size scalars: 44.55 GB read + 2.32 GB written "
-                        "(algorithmic 3.22 GB; the rest is the 16 x 64 B table gathers per scalar of the resident-table design, "
-                        "37 % L2 hits) - profiles/r01_ncu_final.md")
+CSRC = os.path.join(ROOT, "halo2-rsa_b200", "csrc")
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")
+
+
+def kernel_revision(files):
+    """sha1 over the kernel sources a DRAM-traffic capture depends on (tools/traffic_from_ncu.py stamps the same value)"""
+    import hashlib
+    h = hashlib.sha1()
+    for f in files:
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def recorded_traffic(name, files):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch from the last `ncu --set full` capture
+    (profiles/traffic.json, written by tools/traffic_from_ncu.py).  The record carries the revision of the kernel
+    sources it was captured at; if they changed since, the number is refused (null + note) instead of going stale."""
+    try:
+        rec = json.load(open(TRAFFIC_FILE))[name]
+    except Exception:
+        return None, {"traffic_note": "no ncu capture recorded for this kernel (profiles/traffic.json)"}
+    now = kernel_revision(files)
+    if rec.get("kernel_revision") != now:
+        return None, {"traffic_note": f"stale capture refused: recorded at kernel revision {rec.get('kernel_revision')}, sources are now {now}"}
+    return rec["dram_bytes_per_launch"], {"traffic_algorithmic_bytes_of_that_launch": rec.get("algorithmic_bytes_per_launch"),
+                                          "traffic_source": rec.get("source"), "traffic_kernel_revision": now}
+
+
+MSM_SOURCES = ("msm.cu", "ec.cuh", "field.cuh")
+NTT_SOURCES = ("ntt.cu", "field.cuh")
 
 
 def measured_peaks():
@@ -106,12 +130,11 @@ class ClockSampler:
 
 
 def cpu_port_step(samples, threads):
-    """the CPU arm (oracle 'port'): seconds for the MSM / FFT / witness work of `samples` full proofs, sequentially:
-    single-threaded synthesize (as the reference), then on `threads` host threads 31 best_multiexp of 2^17 terms
-    (5 real advice columns; 10 permuted-lookup-like columns = 40 % full-size scalars, 60 % zero, which is what
-    theta-compressed range rows look like; 16 uniform: grand products, random poly, h pieces, GWC witnesses),
-    22 lagrange_to_coeff, 22 coeff_to_extended and 1 extended_to_coeff."""
+    """the CPU arm (oracle 'port'): seconds for `samples` COMPLETE proofs, one after the other, the way the reference's
+    bench proves (benches/bench.rs:319-331): single-threaded synthesize (as the reference's SimpleFloorPlanner pass),
+    then create_proof on `threads` host threads (oracle/plonk_prover.c)."""
     import cpu_oracle as CO
+    import plonk as PL
     import rsa_fixtures as RF
     st = cpu_port_state(threads)
     t0 = time.perf_counter()
@@ -122,16 +145,9 @@ def cpu_port_step(samples, threads):
         assert ok == 1
         adv = t.advice()
         t.free()
-        for col in range(NCOL):
-            CO.best_multiexp(adv[col], st["gl"], threads)
-        for j in range(10):
-            CO.best_multiexp(st["lookup_like"], st["gl"], threads)
-        for j in range(16):
-            CO.best_multiexp(st["uniform"], st["g"] if j >= 7 else st["gl"], threads)
-        for j in range(INTT_PER_PROOF):
-            co = CO.lagrange_to_coeff(adv[j % NCOL] if j < NCOL else st["uniform"], K, threads)
-            CO.coeff_to_extended(co, K, EXT_K, threads)
-        CO.extended_to_coeff(st["ext"], EXT_K, threads)
+        proof, _ = PL.create_proof_c(st["ka"], st["srs"], adv, 0xB200, proof_index=i, nonce=st["nonce"], threads=threads)
+        st["nonce"] += 1
+        st["last_proof"] = proof
     return time.perf_counter() - t0
 
 
@@ -139,18 +155,15 @@ _cpu_state = None
 
 
 def cpu_port_state(threads):
+    """SRS + keygen of the CPU arm (outside every timed region, like ParamsKZG::setup / keygen_pk in the reference's bench)"""
     global _cpu_state
     if _cpu_state is None:
         import cpu_oracle as CO
-        from util import random_fr_np
+        import plonk as PL
         CO.build()
-        n = 1 << K
-        # any 2^17 valid affine points serve as timing bases for the CPU leg (cost does not depend on them)
-        bases = CO.g1_multiples(n, threads)
-        uni = random_fr_np(n, 11)
-        look = uni.copy()
-        look[np.random.default_rng(5).random(n) < 0.6] = 0
-        _cpu_state = {"g": bases, "gl": bases, "uniform": uni, "lookup_like": look, "ext": random_fr_np(1 << EXT_K, 12)}
+        srs = PL.Srs(K)
+        ka = PL.keygen_arrays(PL.circuit_layout(BITS, K), srs, threads)
+        _cpu_state = {"srs": srs, "ka": ka, "nonce": 0, "last_proof": None}
     return _cpu_state
 
 
@@ -162,8 +175,12 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     cpu_port_state(threads)
     sample = 1
+    st = cpu_port_state(threads)
     for _ in range(args.warmup if args.warmup < 1 else 1):
         cpu_port_step(sample, threads)
+    import plonk as PL
+    vk = PL.vk_from_commitments(K, st["ka"]["fixed_commitments"], st["ka"]["sigma_commitments"], st["ka"]["transcript_repr"])
+    assert PL.verify_proof(vk, st["srs"].s, st["last_proof"]), "CPU arm produced a proof its verifier rejects"
     t = 0.0
     for _ in range(args.steps):
         t += cpu_port_step(sample, threads)
@@ -174,11 +191,56 @@ def run_reference(args):
         "dtype": "u64 limbs (BN254 Fr/Fq Montgomery, integer)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_per_step": f"{sample} proof (bounded sample of the 64-instance batch)"},
         "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} proof per step x {args.steps} steps: synthesize on 1 thread + 31 MSM / 45 FFT on {threads} threads; prover glue excluded (upper bound on CPU proofs/s)"},
+                         "sample": f"{sample} complete proof per step x {args.steps} steps: synthesize on 1 thread, then create_proof (31 MSM, 45 FFT, lookups, grand products, quotient, evaluations, multiopen, transcript) on {threads} threads"},
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is Rust (no cargo/rustc in this image): timed arm is oracle/ - the C restatement of its CPU algorithms",
+        "note": "reference is Rust (no cargo/rustc in this image): timed arm is oracle/ - the C restatement of its CPU prover (rsa_witness.c + plonk_prover.c)",
     }
     print(json.dumps(line))
+
+
+def config5_microbench(ctx, torch, stream):
+    """BASELINE configs[4]: standalone BN254 MSM 2^20 (bases (i+1) G, uniform seeded scalars) and forward NTT 2^22
+    (uniform input, omega = ROOT_OF_UNITY^(2^6)), device resident, CUDA events on the library's stream, best and mean of
+    5 after 2 warm-ups; outside the timed region of the headline metric.  GB/s = algorithmic bytes / time."""
+    import cpu_oracle as CO
+    import bn254 as O
+    from util import fr_to_np, random_fr_np
+    peak = (measured_peaks() or {}).get("hbm_gbs", 6650.0)
+
+    def timeit(fn, reps=5):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return min(ts), sum(ts) / len(ts)
+
+    out = {}
+    n = 1 << 20
+    bs = ctx.bases_register(CO.g1_multiples(n))
+    sc = torch.from_numpy(random_fr_np(n, 0x5EED).view(np.int64)).cuda()
+    res = torch.zeros(8, dtype=torch.int64, device="cuda")
+    best, mean = timeit(lambda: ctx.msm_batch_dev(bs, sc.data_ptr(), 1, n, res.data_ptr(), uniform=True))
+    gb = n * MSM_BYTES_PER_TERM / 1e9
+    out["msm_2p20"] = {"ms_best": best, "ms_mean": mean, "algorithmic_GBps": gb / best * 1e3, "frac_of_hbm_peak": gb / best * 1e3 / peak,
+                       "terms_per_s": n / best * 1e3, "workload": "2^20 uniform scalars, bases (i+1)G resident (c = 16 window table)"}
+    bs.free()
+    del sc
+    log_n = 22
+    m = 1 << log_n
+    a = torch.from_numpy(random_fr_np(m, 0x5EED + 1).view(np.int64)).cuda()
+    w = fr_to_np([O.omega_for(log_n)])[0]
+    best, mean = timeit(lambda: ctx.ntt_batch_dev(a.data_ptr(), 1, w, log_n))
+    gb = 2 * m * 32 / 1e9
+    out["ntt_2p22"] = {"ms_best": best, "ms_mean": mean, "algorithmic_GBps": gb / best * 1e3, "frac_of_hbm_peak": gb / best * 1e3 / peak,
+                       "workload": "forward NTT 2^22 in place, natural order in and out"}
+    out["peak_GBps"] = peak
+    return out
 
 
 def main():
@@ -191,6 +253,7 @@ def main():
     ap.add_argument("--workload", default="rsa2048", choices=["rsa2048", "rsa4096"],
                     help="rsa2048 = BASELINE configs[1] (the headline line, default); rsa4096 = configs[2] (RSA-4096, k = 18, batch 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the BASELINE configs[4] microbench (MSM 2^20 / NTT 2^22)")
     args = ap.parse_args()
     global BITS, K, EXT_K, BATCH, WORKLOAD
     if args.workload == "rsa4096":
@@ -303,6 +366,10 @@ def main():
     value = world * batch * args.steps / (ms / 1e3)
     e2e_value = world * batch * args.steps / (ms_e2e / 1e3)
 
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = config5_microbench(ctx, torch, side)
+
     if rank == 0:
         peaks = measured_peaks()
         peak = (peaks or {}).get("hbm_gbs", 6650.0)
@@ -328,9 +395,19 @@ def main():
                                 "how": "bucket entries counted by the library (zero digits and, for the grand-product columns, rows where the "
                                        "column does not change are skipped) / kernel time; peak = 148 SMs x 32 IMAD.WIDE lanes/clk / "
                                        "(9 products x 128 + 1 squaring x 100 IMAD.WIDE) at 1965 MHz"}
-            roof["traffic"] = ACCUM_TRAFFIC_BYTES
-            roof["traffic_algorithmic_bytes_of_that_launch"] = ACCUM_TRAFFIC_VECTORS * n * MSM_BYTES_PER_TERM
-            roof["traffic_source"] = ACCUM_TRAFFIC_SOURCE
+            roof["traffic"], extra_t = recorded_traffic("k_accum_entries", MSM_SOURCES)
+            roof.update(extra_t)
+            if "ntt_pass" in prof:
+                # second entry: the NTT passes, the kernel closest to being HBM relevant.  Algorithmic bytes per transform
+                # = 2 * n * 32 B; `units` recorded by the library = elements per pass launch.
+                nms, ncnt = prof["ntt_pass"]
+                ntt_alg = args.steps * batch * (INTT_PER_PROOF * 2 * n * 32 + (COSET_PER_PROOF + 1) * 2 * (n << (EXT_K - K)) * 32)
+                ntt_ach = ntt_alg / (nms / 1e3) / 1e9
+                tr, extra_n = recorded_traffic("k_ntt_pass", NTT_SOURCES)
+                roof["ntt"] = {"bound": "hbm", "kernel": "k_ntt_pass (all passes of the 45 transforms per proof)", "achieved": ntt_ach, "peak": peak, "unit": "GB/s",
+                               "frac": ntt_ach / peak, "traffic": tr, "ms_per_step": nms / args.steps, "launches_per_step": ncnt / args.steps,
+                               "share_of_step": nms / ms, "algorithmic_bytes_per_step": ntt_alg / args.steps}
+                roof["ntt"].update(extra_n)
         line = {
             "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -343,13 +420,15 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
         }
+        if extra:
+            line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             cpu_port_state(threads)
             sample = 2
             t = cpu_port_step(sample, threads)
             line["cpu_baseline"] = {"value": sample / t, "unit": "proofs/s", "cores": threads, "kind": "port",
-                                    "sample": f"MSM / FFT / witness work of {sample} full proofs, sequential: synthesize on 1 thread, 31 best_multiexp + 45 best_fft restatements per proof on {threads} threads ({t:.1f} s); prover glue excluded, so this is an upper bound on the CPU's proofs/s"}
+                                    "sample": f"{sample} complete proofs of the same workload, one after the other: synthesize on 1 thread + the whole create_proof (oracle/plonk_prover.c) on {threads} threads ({t:.1f} s)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

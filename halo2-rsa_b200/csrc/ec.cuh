@@ -236,7 +236,7 @@ B2R_HD affine_t xyzz_to_affine(const xyzz_t& p) {
         r.y = Fq::zero();
         return r;
     }
-    fe_t t = Fq::inv(Fq::mul(p.zz, p.zzz));
+    fe_t t = Fq::inv_vartime(Fq::mul(p.zz, p.zzz));   // binary Euclid: this sits at the end of every MSM's single-thread tail
     r.x = Fq::mul(p.x, Fq::mul(t, p.zzz));  // X / ZZ
     r.y = Fq::mul(p.y, Fq::mul(t, p.zz));   // Y / ZZZ
     return r;

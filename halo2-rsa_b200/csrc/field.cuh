@@ -492,6 +492,45 @@ struct Field {
         e[0] -= 2u;  // both moduli end in ...01 / ...47: no borrow
         return pow(a, e);
     }
+    // The same inverse by the binary extended Euclid algorithm: ~500 iterations of 256-bit shifts / subtractions on the
+    // ALU instead of 254 squarings + ~127 products on the multiplier.  One thread's Fermat chain is ~380 dependent
+    // Montgomery products (0.2 ms at single-warp latency: the tail of every MSM's bucket reduction); this is ~10x
+    // shorter.  Variable time (public data only).  Input / output in Montgomery form: (aR)^-1 * R^3 * R^-1 = a^-1 R.
+    B2R_HD static fe_t inv_vartime(const fe_t& a) {
+        if (is_zero(a)) return a;
+        uint32_t u[8], v[8], x1[8], x2[8], m[8], t[8];
+        for (int i = 0; i < 8; i++) { u[i] = a.l[i]; v[i] = m[i] = P::MOD(i); x1[i] = x2[i] = 0; }
+        x1[0] = 1;
+        auto is_one = [](const uint32_t* w) {
+            uint32_t o = w[0] ^ 1u;
+            for (int i = 1; i < 8; i++) o |= w[i];
+            return o == 0;
+        };
+        auto shr1 = [](uint32_t* w) {
+            for (int i = 0; i < 7; i++) w[i] = (w[i] >> 1) | (w[i + 1] << 31);
+            w[7] >>= 1;
+        };
+        auto halve_mod = [&](uint32_t* x) {   // x / 2 mod p for x < p (x + p < 2^255: no carry out)
+            if (x[0] & 1u) add8(x, x, m);
+            shr1(x);
+        };
+        while (!is_one(u) && !is_one(v)) {
+            while (!(u[0] & 1u)) { shr1(u); halve_mod(x1); }
+            while (!(v[0] & 1u)) { shr1(v); halve_mod(x2); }
+            if (!sub8(t, u, v)) {   // u >= v
+                for (int i = 0; i < 8; i++) u[i] = t[i];
+                if (sub8(x1, x1, x2)) add8(x1, x1, m);
+            } else {
+                sub8(v, v, u);
+                if (sub8(x2, x2, x1)) add8(x2, x2, m);
+            }
+        }
+        fe_t r;
+        const bool first = is_one(u);
+        for (int i = 0; i < 8; i++) r.l[i] = first ? x1[i] : x2[i];
+        const fe_t r3 = mul(r2(), r2());
+        return mul(r, r3);
+    }
 };
 
 using Fr = Field<FrP>;

@@ -295,9 +295,9 @@ struct DigitLoopBins<C, W, W, LB> {
 // fixed-capacity bins), k_bin_sort finishes each bin in shared memory by the low 8 bits and writes the final sorted
 // list, the keys and the bucket offsets.  A bin that overflows its capacity raises a flag and the group is redone by
 // the general kernels.
-// HB = high bits: 7 (128 bins of 256 buckets) up to 2^17 scalars, 8 (256 bins of 128 buckets) for 2^18, so that a bin
-// holds ~16 K entries either way.
-static constexpr uint32_t BIN_CAP = 20480, BIN_SORT_T = 512, BIN_MAX = 256;
+// HB = high bits: 7 (128 bins of 256 buckets) up to 2^17 scalars, 8 (256 bins of 128 buckets) for 2^18, 9 for 2^19 and
+// 10 (1024 bins of 32 buckets) for 2^20 (BASELINE configs[4]), so that a bin holds ~16 K entries every time.
+static constexpr uint32_t BIN_CAP = 20480, BIN_SORT_T = 512, BIN_MAX = 256 /* buckets per bin */, BIN_HI_MAX = 1024 /* bins per vector */;
 
 template <int C, int HB>
 __global__ void __launch_bounds__(256)
@@ -306,9 +306,10 @@ k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, ui
     constexpr int W = (255 + C - 1) / C;
     constexpr uint32_t HI = 1u << HB, PER = HI / 32;
     __shared__ uint32_t hist[HI], base[HI], lstart[HI + 1];
-    __shared__ uint32_t stage[256 * W];   // the CTA's entries grouped by bin, so that every bin's run leaves as one coalesced store
+    __shared__ uint32_t stage[256 * W];      // the CTA's entries grouped by bin, so that every bin's run leaves as one contiguous store
+    __shared__ uint16_t stage_bin[256 * W];  // bin of every staged entry
     const uint32_t g = blockIdx.y, tid = threadIdx.x, i = blockIdx.x * 256 + tid, lane = tid & 31, wid = tid >> 5;
-    if (tid < HI) hist[tid] = 0;
+    for (uint32_t h = tid; h < HI; h += 256) hist[h] = 0;
     __syncthreads();
     fe_t s = Fr::zero();
     if (i < n) s = ldg_fe(scalars + (size_t)g * n + i);
@@ -323,11 +324,11 @@ k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, ui
         DigitLoopBins<C, 0, W, C - 1 - HB>::run(s, carry, i, n_table, idx_bits, hist, packed, where);
     }
     __syncthreads();
-    if (tid < HI) base[tid] = hist[tid] ? atomicAdd(&bin_fill[(size_t)g * HI + tid], hist[tid]) : 0;
+    for (uint32_t h = tid; h < HI; h += 256) base[h] = hist[h] ? atomicAdd(&bin_fill[(size_t)g * HI + h], hist[h]) : 0;
     if (wid == 7) {   // exclusive scan of the local counts by one warp, PER bins per lane
-        uint32_t cn[PER], tot = 0;
+        uint32_t tot = 0;
 #pragma unroll
-        for (uint32_t q = 0; q < PER; q++) { cn[q] = hist[lane * PER + q]; tot += cn[q]; }
+        for (uint32_t q = 0; q < PER; q++) tot += hist[lane * PER + q];
         uint32_t x = tot;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -336,38 +337,38 @@ k_bin_scatter(const fe_t* __restrict__ scalars, uint32_t n, uint32_t n_table, ui
         }
         uint32_t e = x - tot;
 #pragma unroll
-        for (uint32_t q = 0; q < PER; q++) { lstart[lane * PER + q] = e; e += cn[q]; }
+        for (uint32_t q = 0; q < PER; q++) { lstart[lane * PER + q] = e; e += hist[lane * PER + q]; }
         if (lane == 31) lstart[HI] = x;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < W; j++) {
         if (where[j] == 0xffffffffu) continue;
-        stage[lstart[where[j] >> 16] + (where[j] & 0xffffu)] = packed[j];
+        const uint32_t h = where[j] >> 16, pos = lstart[h] + (where[j] & 0xffffu);
+        stage[pos] = packed[j];
+        stage_bin[pos] = (uint16_t)h;
     }
     __syncthreads();
     uint32_t* mine = bins + (size_t)g * HI * BIN_CAP;
     bool over = false;
-    for (uint32_t h = wid; h < HI; h += 8) {
-        const uint32_t b0 = lstart[h], cnt = lstart[h + 1] - b0, dst = base[h];
-        uint32_t* out = mine + (size_t)h * BIN_CAP;
-        for (uint32_t t = lane; t < cnt; t += 32) {
-            if (dst + t < BIN_CAP) out[dst + t] = stage[b0 + t];
-            else over = true;
-        }
+    const uint32_t total = lstart[HI];
+    for (uint32_t p = tid; p < total; p += 256) {   // neighbours in the stage are neighbours in their bin
+        const uint32_t h = stage_bin[p], dst = base[h] + (p - lstart[h]);
+        if (dst < BIN_CAP) mine[(size_t)h * BIN_CAP + dst] = stage[p];
+        else over = true;
     }
     if (over) atomicOr(flags + g, 1u);
 }
 
 // exclusive scan of the HI bin sizes of every vector -> bin_base[g][0..HI] (bin_base[g][HI] = number of entries)
-__global__ void __launch_bounds__(BIN_MAX) k_bin_prefix(const uint32_t* __restrict__ bin_fill, uint32_t* __restrict__ bin_base, uint32_t* __restrict__ off,
-                                                        uint32_t B, uint32_t HI) {
-    __shared__ uint32_t sh[BIN_MAX];
+__global__ void __launch_bounds__(BIN_HI_MAX) k_bin_prefix(const uint32_t* __restrict__ bin_fill, uint32_t* __restrict__ bin_base, uint32_t* __restrict__ off,
+                                                           uint32_t B, uint32_t HI) {
+    __shared__ uint32_t sh[BIN_HI_MAX];
     const uint32_t g = blockIdx.x, t = threadIdx.x;
     const uint32_t v = t < HI ? min(bin_fill[(size_t)g * HI + t], BIN_CAP) : 0;
     sh[t] = v;
     __syncthreads();
-    for (uint32_t d = 1; d < BIN_MAX; d <<= 1) {
+    for (uint32_t d = 1; d < BIN_HI_MAX; d <<= 1) {
         const uint32_t o = t >= d ? sh[t - d] : 0;
         __syncthreads();
         sh[t] += o;
@@ -541,6 +542,160 @@ k_accum_entries(const affine_t* __restrict__ table, const uint32_t* __restrict__
     emit_run(cur, acc, begins, end == off[cur + 1], first, bk, sk, sp, slot0);
 }
 
+// ---- the same walk with the table points staged through shared memory by the TMA engine ---------------------------
+// The 64-byte table point of entry pos + 1 is fetched while entry pos is being added: every lane issues one
+// cp.async.bulk (global -> its own shared-memory slot) that completes on its warp's mbarrier for that ring stage, and
+// reads the point back with four conflict-free LDS.128 right where the addition needs it.  Unlike the register prefetch
+// (PF above: 16 more live registers, spills at 127) the point in flight costs no registers, so the DRAM / L2 latency of
+// the gather (the table is 128 MiB, 37 % L2 hits) is hidden behind a full mixed addition instead of being exposed at
+// the top of every iteration.  Ring: RING_D stages x 128 lanes x 80 bytes (64-byte point + 16 bytes of padding: eight
+// consecutive lanes then start in eight different 16-byte bank groups).
+static constexpr uint32_t RING_D = 2, RING_SLOT = 80;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ affine_t lds_affine(uint32_t addr) {
+    affine_t r;
+    uint32_t* w = r.x.l;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(addr + 16));
+    w = r.y.l;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr + 32));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(addr + 48));
+    return r;
+}
+
+__device__ __forceinline__ void ldgsts64(uint32_t dst, const void* src) {
+    const char* s = (const char*)src;
+#pragma unroll
+    for (int j = 0; j < 4; j++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * j), "l"(s + 16 * j) : "memory");
+}
+template <int L, int MINB, bool BULK>
+__global__ void __launch_bounds__(128, MINB)
+k_accum_entries_ring(const affine_t* __restrict__ table, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ keys,
+                     size_t ent_stride, const uint32_t* __restrict__ offsets, uint32_t B, uint32_t nchunks, xyzz_t* buckets,
+                     uint32_t* slot_keys, xyzz_t* slot_pts, size_t slot_stride) {
+    __shared__ __align__(16) uint8_t ring[RING_D * 128 * RING_SLOT];
+    __shared__ __align__(8) uint64_t bars[RING_D * 4];
+    const uint32_t g = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t t = blockIdx.x * blockDim.x + tid;
+    if (BULK) {
+        if (lane == 0) {
+            for (uint32_t s = 0; s < RING_D; s++) mbar_init(smem_addr(&bars[s * 4 + wid]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    const uint32_t* off = offsets + (size_t)g * (B + 1);
+    const uint32_t* ent = entries + (size_t)g * ent_stride;
+    const uint32_t* key = keys + (size_t)g * ent_stride;
+    xyzz_t* bk = buckets + (size_t)g * B;
+    uint32_t* sk = slot_keys + (size_t)g * slot_stride;
+    xyzz_t* sp = slot_pts + (size_t)g * slot_stride;
+    const size_t slot0 = 2 * (size_t)t;
+    if (t < nchunks) {
+        sk[slot0] = SLOT_INVALID;
+        sk[slot0 + 1] = SLOT_INVALID;
+    }
+    const uint32_t E = off[B];
+    const uint32_t start = t * L;
+    // no early return: the warp-wide votes below need every lane; a lane without entries has end == start
+    const bool live = t < nchunks && start < E;
+    const uint32_t end = live ? min(start + (uint32_t)L, E) : start;
+    uint32_t ring_base[RING_D], bar_addr[RING_D];
+#pragma unroll
+    for (uint32_t s = 0; s < RING_D; s++) {
+        ring_base[s] = smem_addr(ring) + (s * 128 + tid) * RING_SLOT;
+        bar_addr[s] = smem_addr(&bars[s * 4 + wid]);
+    }
+    uint32_t cur = 0, e_next = 0, k_next = 0;
+    bool begins = false, first = true;
+    xyzz_t acc = xyzz_identity();
+    if (live) {
+        cur = key[start];
+        begins = (off[cur] == start);
+        const uint32_t e = ent[start];
+        acc = xyzz_from_affine_signed(ldg_affine(table + (e & 0x7fffffffu)), (e >> 31) != 0);
+        k_next = cur;
+    }
+    // stage for i = 1 (entry start + 1)
+    {
+        const bool v1 = start + 1 < end;
+        if (v1) {
+            e_next = ent[start + 1];
+            k_next = key[start + 1];
+        }
+        if (BULK) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, v1);
+            if (lane == 0 && bal) mbar_expect_tx(bar_addr[1 % RING_D], 64u * __popc(bal));
+            __syncwarp();
+            if (v1) bulk_g2s(ring_base[1 % RING_D], table + (e_next & 0x7fffffffu), 64u, bar_addr[1 % RING_D]);
+        } else {
+            if (v1) ldgsts64(ring_base[1 % RING_D], table + (e_next & 0x7fffffffu));
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    }
+#pragma unroll 1
+    for (uint32_t i = 1; i < (uint32_t)L; i++) {
+        const uint32_t pos = start + i;
+        const bool v = pos < end, vn = pos + 1 < end;
+        const uint32_t bal = __ballot_sync(0xffffffffu, v);
+        if (!bal) break;
+        const uint32_t ec = e_next, kc = k_next;
+        // issue the gather of entry pos + 1 into the other stage (its previous content, entry pos - 1, was consumed in
+        // the previous iteration), then wait for this iteration's stage
+        if (vn) {
+            e_next = ent[pos + 1];
+            k_next = key[pos + 1];
+        }
+        const uint32_t sn = (i + 1) % RING_D, sc = i % RING_D;
+        if (BULK) {
+            const uint32_t baln = __ballot_sync(0xffffffffu, vn);
+            if (lane == 0 && baln) mbar_expect_tx(bar_addr[sn], 64u * __popc(baln));
+            __syncwarp();
+            if (vn) bulk_g2s(ring_base[sn], table + (e_next & 0x7fffffffu), 64u, bar_addr[sn]);
+            mbar_wait(bar_addr[sc], ((i - (sc ? sc : RING_D)) / RING_D) & 1u);   // parity of this stage's use count
+        } else {
+            if (vn) ldgsts64(ring_base[sn], table + (e_next & 0x7fffffffu));
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the group just committed has landed
+        }
+        if (v) {
+            const affine_t p = lds_affine(ring_base[sc]);
+            if (kc != cur) {
+                emit_run(cur, acc, begins, true, first, bk, sk, sp, slot0);
+                first = false;
+                begins = true;
+                cur = kc;
+                acc = xyzz_from_affine_signed(p, (ec >> 31) != 0);
+            } else {
+                xyzz_madd_ls(acc, p, (ec >> 31) != 0);
+            }
+        }
+    }
+    if (live) emit_run(cur, acc, begins, end == off[cur + 1], first, bk, sk, sp, slot0);
+}
+
 // upper levels: the same walk over a slot list (key + XYZZ partial sum per slot)
 template <int L>
 __global__ void __launch_bounds__(128)
@@ -585,6 +740,32 @@ k_accum_slots(const uint32_t* __restrict__ in_keys, const xyzz_t* __restrict__ i
     if (have) emit_run(cb, acc, begins, ends, first, bk, sk, sp, slot0);
 }
 
+// One thread per bucket gathers the chunk-boundary partial sums k_accum_entries left in the level-A slot list, in one
+// launch instead of the log_16 levels of k_accum_slots (seven launches of latency-bound 16-addition chains for a
+// standalone 2^20 MSM: 0.39 ms).  Bucket b covers entries [off[b], off[b+1]) = chunks t0 .. t1 of L entries; it was
+// stored directly if it lies inside one chunk, otherwise chunk t holds its partial sum in slot 2t (the bucket is the
+// first run of the chunk) or 2t + 1 (only possible for t0, when the bucket starts inside the chunk).  Used behind the
+// binned sort, whose bins bound a bucket to a few hundred chunks; arbitrary distributions keep the level scheme.
+template <int L>
+__global__ void __launch_bounds__(128)
+k_bucket_fixup(const uint32_t* __restrict__ offsets, uint32_t B, const xyzz_t* __restrict__ slot_pts, size_t slot_stride, xyzz_t* __restrict__ buckets) {
+    const uint32_t g = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t* off = offsets + (size_t)g * (B + 1);
+    const uint32_t lo = off[b], hi = off[b + 1];
+    if (hi <= lo) return;
+    const uint32_t t0 = lo / L, t1 = (hi - 1) / L;
+    if (t0 == t1) return;   // complete inside one chunk: stored by k_accum_entries
+    const xyzz_t* sp = slot_pts + (size_t)g * slot_stride;
+    xyzz_t acc = ld_xyzz(sp + 2 * (size_t)t0 + (lo == t0 * L ? 0 : 1));
+#pragma unroll 1
+    for (uint32_t t = t0 + 1; t <= t1; t++) {
+        const xyzz_t q = ld_xyzz(sp + 2 * (size_t)t);
+        xyzz_add(acc, q);
+    }
+    st_xyzz(buckets + (size_t)g * B + b, acc);
+}
+
 // ---- sum_b (b+1) * B_b -------------------------------------------------------------------
 // Three levels of running sums, every thread busy in the two large ones (the first version combined 128 threads
 // per CTA with shared-memory scans and a one-thread double-and-add tail: 1.9x the additions, most of them in
@@ -613,6 +794,48 @@ k_br_level1(const xyzz_t* __restrict__ buckets, uint32_t B, uint32_t nseg, xyzz_
     if (live) {
         st_xyzz(S1 + (size_t)g * nseg + s, run);
         st_xyzz(A1 + (size_t)g * nseg + s, acc);
+    }
+}
+
+// Level 1 for a single vector (or a handful): the per-thread running sums above are a chain of 64 dependent full
+// additions with only nseg = B / 32 threads per vector (8 CTAs at c = 16: 0.48 ms of latency for a standalone 2^20 MSM,
+// profiles/r01_ncu_config5.md).  Here a WARP owns the 32 buckets of a segment: inclusive suffix scan over the lanes
+// (5 shuffle steps) gives T_l = sum_{j >= l} B_j, so S1 = T_0 and A1 = sum_l T_l (bucket d counted d + 1 times), a
+// second 5-step tree sum.  10 dependent additions instead of 64, 5x the total work - used when the launch would
+// otherwise leave most of the GPU idle.
+__device__ __forceinline__ xyzz_t shfl_down_xyzz(const xyzz_t& v, uint32_t d) {
+    xyzz_t r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], d);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], d);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], d);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], d);
+    }
+    return r;
+}
+__global__ void __launch_bounds__(128)
+k_br_level1_warp(const xyzz_t* __restrict__ buckets, uint32_t B, uint32_t nseg, uint32_t total_seg, xyzz_t* __restrict__ S1, xyzz_t* __restrict__ A1) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= total_seg) return;   // whole warps leave together
+    const uint32_t g = w / nseg, sgm = w % nseg;
+    xyzz_t run = ld_xyzz(buckets + (size_t)g * B + (size_t)sgm * BR_PER1 + lane);
+#pragma unroll 1
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        xyzz_t o = shfl_down_xyzz(run, d);
+        if (lane + d >= 32) o = xyzz_identity();
+        xyzz_add_ls(run, o);
+    }
+    xyzz_t acc = run;   // T_lane
+#pragma unroll 1
+    for (uint32_t d = 16; d > 0; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(acc, d);
+        if (lane >= d) o = xyzz_identity();   // only lanes < d keep a meaningful partial sum
+        xyzz_add_ls(acc, o);
+    }
+    if (lane == 0) {
+        st_xyzz(S1 + (size_t)g * nseg + sgm, run);
+        st_xyzz(A1 + (size_t)g * nseg + sgm, acc);
     }
 }
 
@@ -698,6 +921,65 @@ k_br_level3(const xyzz_t* __restrict__ L2, uint32_t nu, affine_t* __restrict__ o
     }
 }
 
+// Levels 2 and 3 for a single vector at c = 16 (nseg = 1024): a warp per 32 segments, then one CTA of three warps.
+//   level 2  S2_u = sum_l S1,  A2_u = sum_l l * S1_{32u+l} = sum_{l >= 1} T_l,  P1_u = sum_l A1      (u < 32)
+//   level 3  W = sum_u u * S2_u, SA = sum A2, SP = sum P1 by warps 0, 1, 2 side by side; result = SP + 32 (SA + 32 W)
+__device__ __forceinline__ xyzz_t warp_tree_sum(xyzz_t v, uint32_t lane) {
+#pragma unroll 1
+    for (uint32_t d = 16; d > 0; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(v, d);
+        if (lane >= d) o = xyzz_identity();
+        xyzz_add_ls(v, o);
+    }
+    return v;   // lane 0
+}
+// -> lane 0: sum_{l >= 1} T_l = sum_l l * v_l ; total = sum_l v_l
+__device__ __forceinline__ xyzz_t warp_weighted_sum(xyzz_t v, uint32_t lane, xyzz_t& total) {
+#pragma unroll 1
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        xyzz_t o = shfl_down_xyzz(v, d);
+        if (lane + d >= 32) o = xyzz_identity();
+        xyzz_add_ls(v, o);
+    }
+    total = v;   // lane 0: T_0
+    if (lane == 0) v = xyzz_identity();
+    return warp_tree_sum(v, lane);
+}
+__global__ void __launch_bounds__(128)
+k_br_level2_warp(const xyzz_t* __restrict__ S1, const xyzz_t* __restrict__ A1, uint32_t total_u, xyzz_t* __restrict__ L2) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= total_u) return;
+    xyzz_t tot;
+    const xyzz_t a2 = warp_weighted_sum(ld_xyzz(S1 + (size_t)w * 32 + lane), lane, tot);
+    const xyzz_t p1 = warp_tree_sum(ld_xyzz(A1 + (size_t)w * 32 + lane), lane);
+    if (lane == 0) {
+        xyzz_t* o = L2 + (size_t)w * 3;
+        st_xyzz(o, tot);
+        st_xyzz(o + 1, a2);
+        st_xyzz(o + 2, p1);
+    }
+}
+__global__ void __launch_bounds__(96)
+k_br_level3_warp(const xyzz_t* __restrict__ L2 /* [G][32][3] */, affine_t* __restrict__ out) {
+    __shared__ uint4 smem_raw[3 * sizeof(xyzz_t) / sizeof(uint4)];
+    xyzz_t* sm = reinterpret_cast<xyzz_t*>(smem_raw);
+    const uint32_t g = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const xyzz_t v = ld_xyzz(L2 + ((size_t)g * 32 + lane) * 3 + wid);
+    xyzz_t r, tot;
+    if (wid == 0) r = warp_weighted_sum(v, lane, tot);   // W
+    else r = warp_tree_sum(v, lane);                     // SA, SP
+    if (lane == 0) sm[wid] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        xyzz_t acc = sm[0];
+        for (int i = 0; i < 5; i++) acc = xyzz_double(acc);
+        xyzz_add(acc, sm[1]);
+        for (int i = 0; i < 5; i++) acc = xyzz_double(acc);
+        xyzz_add(acc, sm[2]);
+        out[g] = xyzz_to_affine(acc);
+    }
+}
+
 static uint32_t pick_window(size_t n) {
     if (n <= ((size_t)1 << 10)) return 10;
     if (n <= ((size_t)1 << 14)) return 13;
@@ -707,7 +989,22 @@ static uint32_t pick_window(size_t n) {
 
 static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_dev, size_t G, size_t n, affine_t* out_dev, bool uniform) {
     const uint32_t c = bs->c, W = bs->W, B = 1u << (c - 1);
-    constexpr uint32_t L1 = MSM_L1, L2 = 16;
+    constexpr uint32_t L2 = 16;
+    // entries per accumulation thread.  A batch fills the GPU many times over whatever the chunk length; a single vector
+    // is a handful of waves of 4 CTAs x 148 SMs, and a last wave that is 46 % full (2^20 scalars at 64 entries: 3.46
+    // waves) costs 13 % of the kernel - pick the chunk length whose CTA count comes closest below a whole number of waves
+    uint32_t L1 = MSM_L1;
+    const char* variant_env = getenv("B2R_MSM_VARIANT");  // tuning hook: 1 = register prefetch, 3 / 4 = shared-memory ring (fixed chunk length)
+    const int variant = variant_env ? atoi(variant_env) : 0;
+    if (G <= 4 && variant < 3) {
+        const double per_wave = 4.0 * ctx->sm_count;
+        double best_eff = 0;
+        for (uint32_t cand : {56u, 64u, 74u}) {
+            const double ctas = (double)G * (double)(((n * W + cand - 1) / cand + 127) / 128);
+            const double waves = ctas / per_wave, eff = waves / (double)(uint64_t)(waves + 0.999999);
+            if (eff > best_eff + 1e-9) { best_eff = eff; L1 = cand; }
+        }
+    }
     const size_t ent_cap = (size_t)n * W;
     const uint32_t nch1 = (uint32_t)((ent_cap + L1 - 1) / L1);
     const size_t slotsA = 2 * (size_t)nch1;
@@ -762,9 +1059,11 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     while (((size_t)1 << idx_bits) < (size_t)bs->n * W) idx_bits++;
     const char* bin_env = getenv("B2R_MSM_BINSORT");   // "0" disables, "1" forces (tests); read per call so a test can toggle it
     const bool want_bins = bin_env ? bin_env[0] == '1' : uniform;
-    // bins of ~n * W / HI entries: 128 bins up to 2^17 scalars, 256 bins up to 2^18 (capacity 20480 per bin, 25 % slack)
-    const uint32_t HI = (size_t)n * W * 9 / 8 <= (size_t)128 * BIN_CAP ? 128u : 256u;
-    if (want_bins && c == 16 && idx_bits + 9 <= 32 && (size_t)n * W * 9 / 8 <= (size_t)HI * BIN_CAP) {
+    // bins of ~n * W / HI entries (capacity 20480 per bin, 25 % slack): 128 bins up to 2^17 scalars ... 1024 bins at 2^20
+    uint32_t HB = 7;
+    while (HB < 10 && (size_t)n * W * 9 / 8 > ((size_t)BIN_CAP << HB)) HB++;
+    const uint32_t HI = 1u << HB;
+    if (want_bins && c == 16 && idx_bits + 1 + (c - 1 - HB) <= 32 && (size_t)n * W * 9 / 8 <= (size_t)HI * BIN_CAP) {
         uint32_t* bins = nullptr;
         const size_t fill_bytes = (G * HI * 4 + 255) & ~(size_t)255, base_bytes = (G * (HI + 1) * 4 + 255) & ~(size_t)255;
         B2R_TRY(scratch_get(ctx, SC_MSM_B, fill_bytes + base_bytes + 256 + G * (size_t)HI * BIN_CAP * 4 + G * 4, (void**)&bins));
@@ -774,10 +1073,14 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
         uint32_t* bin_data = (uint32_t*)((char*)bins + fill_bytes + base_bytes + 256 + ((G * 4 + 255) & ~(size_t)255));
         B2R_CUDA(ctx, cudaMemsetAsync(bins, 0, fill_bytes + base_bytes + 256 + ((G * 4 + 255) & ~(size_t)255), st));
         { KTimer kt(ctx, "msm_scatter", (double)G * n);
-        if (HI == 128) k_bin_scatter<16, 7><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags);
-        else k_bin_scatter<16, 8><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags);
+        switch (HB) {
+            case 7: k_bin_scatter<16, 7><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags); break;
+            case 8: k_bin_scatter<16, 8><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags); break;
+            case 9: k_bin_scatter<16, 9><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags); break;
+            default: k_bin_scatter<16, 10><<<gd, 256, 0, st>>>(scalars_dev, (uint32_t)n, (uint32_t)bs->n, idx_bits, bin_fill, bin_data, bflags); break;
+        }
         B2R_LAUNCH_CHECK(ctx);
-        k_bin_prefix<<<(unsigned)G, BIN_MAX, 0, st>>>(bin_fill, bin_base, off, B, HI);
+        k_bin_prefix<<<(unsigned)G, BIN_HI_MAX, 0, st>>>(bin_fill, bin_base, off, B, HI);
         B2R_LAUNCH_CHECK(ctx);
         // function attributes are per device: set on every call (a process may hold one context per GPU)
         B2R_CUDA(ctx, cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BIN_CAP * 4)));
@@ -800,19 +1103,37 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     }
     { KTimer kt(ctx, "msm_accum_entries", entries_total);
     {
-        const char* ov = getenv("B2R_MSM_VARIANT");  // tuning hook (occupancy / prefetch variants)
-        const int variant = ov ? atoi(ov) : 0;
         const dim3 ga((nch1 + 127) / 128, (unsigned)G);
-#define B2R_ACC(MINB, PF) k_accum_entries<L1, MINB, PF><<<ga, 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa, slotsA)
+#define B2R_ACC(MINB, PF)                                                                                                        \
+    do {                                                                                                                     \
+        if (L1 == 56) k_accum_entries<56, MINB, PF><<<ga, 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa, slotsA);      \
+        else if (L1 == 74) k_accum_entries<74, MINB, PF><<<ga, 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa, slotsA); \
+        else k_accum_entries<MSM_L1, MINB, PF><<<ga, 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa, slotsA);           \
+    } while (0)
         // measured on B200 (64 x 2^17 uniform scalars, tools/microbench.py): 4 CTAs/SM without the point prefetch 22.7 ms,
         // with it 24.1 ms (spills); 5 or 6 CTAs/SM (96 / 80 registers, spills) 23.5 - 24.0 ms
         switch (variant) {
             case 1: B2R_ACC(4, true); break;
+            case 3:   // table points staged through a shared-memory ring by per-lane cp.async.bulk + mbarrier
+                k_accum_entries_ring<MSM_L1, 4, true><<<ga, 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa, slotsA);
+                break;
+            case 4:   // the same ring filled by LDGSTS (cp.async) groups
+                k_accum_entries_ring<MSM_L1, 4, false><<<ga, 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa, slotsA);
+                break;
             default: B2R_ACC(4, false); break;
         }
 #undef B2R_ACC
     } }
     B2R_LAUNCH_CHECK(ctx);
+    if (sorted && G <= 4) {   // binned sort succeeded: every bucket spans a bounded number of chunks - one fixup launch
+        // (a handful of vectors only: across a large batch the per-bucket loops diverge and the level scheme below is faster)
+        { KTimer kt(ctx, "msm_accum_slots");
+        const dim3 gf((B + 127) / 128, (unsigned)G);
+        if (L1 == 56) k_bucket_fixup<56><<<gf, 128, 0, st>>>(off, B, pa, slotsA, bk);
+        else if (L1 == 74) k_bucket_fixup<74><<<gf, 128, 0, st>>>(off, B, pa, slotsA, bk);
+        else k_bucket_fixup<MSM_L1><<<gf, 128, 0, st>>>(off, B, pa, slotsA, bk); }
+        B2R_LAUNCH_CHECK(ctx);
+    } else {
     // upper levels: ping-pong slot lists until one chunk remains
     const uint32_t* ik = ka;
     const xyzz_t* ip = pa;
@@ -834,14 +1155,24 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
         M = 2 * nch;
         to_b = !to_b;
     }
+    }
+    const bool warp_reduce = nseg == 1024 && G * nseg < (size_t)ctx->sm_count * 128;   // c = 16, a handful of vectors
     { KTimer kt(ctx, "msm_bucket_reduce");
-    k_br_level1<<<dim3((nseg + 127) / 128, (unsigned)G), 128, 0, st>>>(bk, B, nseg, s1, a1);
+    static_assert(BR_PER1 == 32, "k_br_level1_warp maps one lane to one bucket of a segment");
+    if (G * nseg < (size_t)ctx->sm_count * 128) {   // fewer level-1 threads than one CTA per SM: a warp per segment instead
+        const uint32_t total_seg = (uint32_t)(G * nseg);
+        k_br_level1_warp<<<(total_seg + 3) / 4, 128, 0, st>>>(bk, B, nseg, total_seg, s1, a1);
+    } else {
+        k_br_level1<<<dim3((nseg + 127) / 128, (unsigned)G), 128, 0, st>>>(bk, B, nseg, s1, a1);
+    }
     B2R_LAUNCH_CHECK(ctx);
     const uint32_t total = (uint32_t)(G * nu);
-    k_br_level2<<<(total + 127) / 128, 128, 0, st>>>(s1, a1, nseg, nu, total, l2); }
+    if (warp_reduce) k_br_level2_warp<<<(unsigned)((G * 32 + 3) / 4), 128, 0, st>>>(s1, a1, (uint32_t)(G * 32), l2);
+    else k_br_level2<<<(total + 127) / 128, 128, 0, st>>>(s1, a1, nseg, nu, total, l2); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_final");
-    k_br_level3<<<(unsigned)G, BR_T3, 0, st>>>(l2, nu, out_dev); }
+    if (warp_reduce) k_br_level3_warp<<<(unsigned)G, 96, 0, st>>>(l2, out_dev);
+    else k_br_level3<<<(unsigned)G, BR_T3, 0, st>>>(l2, nu, out_dev); }
     B2R_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -849,7 +1180,7 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
 static size_t msm_group_bytes(const b2r_bases* bs, size_t n) {
     const uint32_t W = bs->W, B = 1u << (bs->c - 1);
     size_t ent_cap = n * W;
-    size_t nch1 = (ent_cap + MSM_L1 - 1) / MSM_L1, slotsA = 2 * nch1, slotsB = 2 * ((slotsA + 15) / 16);
+    size_t nch1 = (ent_cap + 55) / 56 /* the shortest chunk length msm_group may pick */, slotsA = 2 * nch1, slotsB = 2 * ((slotsA + 15) / 16);
     return 3 * (size_t)B * 4 + ent_cap * 8 + (size_t)B * 128 + (slotsA + slotsB) * 132 + ((size_t)B / 16 + (size_t)B / 64 + 8) * 128 + 4096 * 8;   // (+ 10 - 20 MiB per vector in the second arena for the binned sort)
 }
 

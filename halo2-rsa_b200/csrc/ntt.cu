@@ -13,6 +13,7 @@
 // out index q + s*(R*p' + bitrev_S(r)).  No bit-reversal pass, natural order in and out.
 // HBM traffic = 2 * n * 32 B per pass (+ the twiddle table, L2 resident for n <= 2^20).
 // Scaling (1/n) and the coset ZETA-power twists are fused into the first load / last store.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -75,33 +76,146 @@ __device__ __forceinline__ void st_fe(fe_t* p, const fe_t& v) {
     q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-template <int S>
-__global__ void __launch_bounds__(256, 4) k_ntt_pass(const NttPassArgs A) {
-    constexpr uint32_t R = 1u << S;
-    // shared tile, split into the low and the high 16 bytes of every element: a warp's 128-bit accesses then touch
-    // consecutive banks (32-byte elements accessed whole are a 2-way bank conflict on every load and store)
-    extern __shared__ uint4 smem_raw[];
-    uint4* const sm_lo = smem_raw;
-    uint4* const sm_hi = smem_raw + ((size_t)(1u << S) << A.log_c);
-    auto lds = [&](uint32_t idx) {
-        const uint4 a = sm_lo[idx], b = sm_hi[idx];
+// Shared-memory tile accessors.  A tile holds R rows x C columns of field elements, element (r, c) at index r * C + c.
+//  SplitTile    the tile split into the low and the high 16 bytes of every element: a warp's 128-bit accesses then touch
+//               consecutive banks (32-byte elements accessed whole are a 2-way bank conflict on every load and store)
+//  SwizzledTile the image a TMA tensor copy with CU_TENSOR_MAP_SWIZZLE_128B leaves: 128-byte lines of 4 elements, the
+//               16-byte chunk j of line L stored at chunk j ^ (L & 7) - also conflict free for 32 consecutive elements
+struct SplitTile {
+    uint4 *lo, *hi;
+    __device__ __forceinline__ fe_t ld(uint32_t idx) const {
+        const uint4 a = lo[idx], b = hi[idx];
         fe_t r;
         r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
         r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
         return r;
-    };
-    auto sts = [&](uint32_t idx, const fe_t& v) {
-        sm_lo[idx] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-        sm_hi[idx] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-    };
+    }
+    __device__ __forceinline__ void st(uint32_t idx, const fe_t& v) const {
+        lo[idx] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        hi[idx] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+};
+struct SwizzledTile {
+    uint4* base;  // 1024-byte aligned
+    __device__ __forceinline__ uint32_t chunk(uint32_t idx) const {
+        const uint32_t line = idx >> 2;
+        return (line << 3) + (((idx & 3u) << 1) ^ (line & 7u));
+    }
+    __device__ __forceinline__ fe_t ld(uint32_t idx) const {
+        const uint32_t c = chunk(idx);
+        const uint4 a = base[c], b = base[c ^ 1u];
+        fe_t r;
+        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+        return r;
+    }
+    __device__ __forceinline__ void st(uint32_t idx, const fe_t& v) const {
+        const uint32_t c = chunk(idx);
+        base[c] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        base[c ^ 1u] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+};
+
+// ---- S radix-2 stages on a tile in shared memory (decimation in frequency, in place), two stages per round trip: a
+// thread takes rows r0, r0+q, r0+2q, r0+3q (q = a quarter of the current block), does the two butterflies of stage i and
+// the two of stage i+1 in registers (4 twiddle products, as two radix-2 stages would) and writes the 4 rows back:
+// half the shared-memory traffic and barriers of the plain radix-2 loop.  Ends with a barrier.
+template <int S, class Tile>
+__device__ __forceinline__ void ntt_tile_stages(const NttPassArgs& A, const Tile& tile, uint32_t c0) {
+    constexpr uint32_t R = 1u << S;
     const uint32_t T = blockDim.x, tid = threadIdx.x;
-    const uint32_t log_c = A.log_c, C = 1u << log_c, cmask = C - 1;
+    const uint32_t log_c = A.log_c, cmask = (1u << log_c) - 1;
+    const uint32_t log_cols = A.log_n - S;  // columns = n / R
+    uint32_t i = 0;
+#pragma unroll 1
+    for (; i + 1 < S; i += 2) {
+        const uint32_t log_q = S - 2 - i, q = 1u << log_q;
+        for (uint32_t g = tid; g < ((R / 4) << log_c); g += T) {
+            const uint32_t c = g & cmask, gf = g >> log_c;
+            const uint32_t blk = gf >> log_q, rp = gf & (q - 1);
+            const uint32_t i0 = ((((blk << (log_q + 2)) + rp)) << log_c) + c, st = q << log_c;
+            const uint32_t base = ((c0 + c) >> A.log_s) << A.log_s;  // s * p'
+            const uint32_t ea = (base + (rp << log_cols)) << i;          // stage i, rows (r0, r0 + 2q)
+            const uint32_t eb = (base + ((rp + q) << log_cols)) << i;    // stage i, rows (r0 + q, r0 + 3q)
+            const uint32_t ec = ea << 1;                                 // stage i + 1, both pairs
+            const fe_t a0 = tile.ld(i0), a1 = tile.ld(i0 + st), a2 = tile.ld(i0 + 2 * st), a3 = tile.ld(i0 + 3 * st);
+            const fe_t u0 = Fr::add(a0, a2), u1 = Fr::add(a1, a3);
+            fe_t d0 = Fr::sub(a0, a2), d1 = Fr::sub(a1, a3);
+            if (ea) d0 = Fr::mul(d0, ld_fe_nc(A.tw + ea));
+            // zero-padded first pass (coeff_to_extended: 3/4 of the rows are zero): a1 = a3 = 0 in the first round, 0 * w = 0
+            if (!Fr::is_zero(d1)) d1 = Fr::mul(d1, ld_fe_nc(A.tw + eb));
+            const fe_t wc = ld_fe_nc(A.tw + ec);
+            tile.st(i0, Fr::add(u0, u1));
+            tile.st(i0 + 2 * st, Fr::add(d0, d1));
+            fe_t v1 = Fr::sub(u0, u1), v3 = Fr::sub(d0, d1);
+            if (ec) {
+                v1 = Fr::mul(v1, wc);
+                v3 = Fr::mul(v3, wc);
+            }
+            tile.st(i0 + st, v1);
+            tile.st(i0 + 3 * st, v3);
+        }
+        __syncthreads();
+    }
+    if (i < S) {  // odd S: one radix-2 stage left (half = 1)
+        for (uint32_t b = tid; b < ((R / 2) << log_c); b += T) {
+            const uint32_t c = b & cmask, bf = b >> log_c;
+            const uint32_t i0 = ((bf << 1) << log_c) + c, i1 = i0 + (1u << log_c);
+            const uint32_t e = (((c0 + c) >> A.log_s) << A.log_s) << i;
+            const fe_t a = tile.ld(i0), bb = tile.ld(i1);
+            fe_t d = Fr::sub(a, bb);
+            if (e) d = Fr::mul(d, ld_fe_nc(A.tw + e));
+            tile.st(i0, Fr::add(a, bb));
+            tile.st(i1, d);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- store: local row r holds output digit t = bitrev_S(r)
+template <int S, class Tile>
+__device__ __forceinline__ void ntt_tile_store(const NttPassArgs& A, const Tile& tile, uint32_t c0, fe_t* y) {
+    constexpr uint32_t R = 1u << S;
+    const uint32_t T = blockDim.x, tid = threadIdx.x;
+    const uint32_t log_c = A.log_c, cmask = (1u << log_c) - 1;
+    const uint32_t smask = (1u << A.log_s) - 1;
+    if (A.log_s == 0) {
+        // first pass: out index = R*col + t, make t the fastest index for contiguous stores
+        for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
+            uint32_t t = idx & (R - 1), c = idx >> S;
+            uint32_t r = __brev(t) >> (32 - S);
+            fe_t v = tile.ld((r << log_c) + c);
+            uint32_t oi = ((c0 + c) << S) + t;
+            if (A.post) v = Fr::mul(v, A.post3[oi % 3u]);
+            st_fe(y + oi, v);
+        }
+    } else {
+        for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
+            uint32_t r = idx >> log_c, c = idx & cmask;
+            uint32_t t = __brev(r) >> (32 - S);
+            uint32_t col = c0 + c, q = col & smask, pp = col >> A.log_s;
+            uint32_t oi = q + (pp << (A.log_s + S)) + (t << A.log_s);
+            fe_t v = tile.ld(idx);
+            if (A.post) v = Fr::mul(v, A.post3[oi % 3u]);
+            st_fe(y + oi, v);
+        }
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 4) k_ntt_pass(const NttPassArgs A) {
+    constexpr uint32_t R = 1u << S;
+    extern __shared__ uint4 smem_raw[];
+    SplitTile tile;
+    tile.lo = smem_raw;
+    tile.hi = smem_raw + ((size_t)(1u << S) << A.log_c);
+    const uint32_t T = blockDim.x, tid = threadIdx.x;
+    const uint32_t log_c = A.log_c, cmask = (1u << log_c) - 1;
     const uint32_t log_cols = A.log_n - S;  // columns = n / R
     const uint32_t c0 = blockIdx.x << log_c;
     const fe_t* x = A.in_inner ? A.x + (uint64_t)(blockIdx.y / A.in_inner) * A.in_stride2 + (uint64_t)(blockIdx.y % A.in_inner) * A.in_stride
                                : A.x + (uint64_t)blockIdx.y * A.in_stride;
     fe_t* y = A.y + (uint64_t)blockIdx.y * A.out_stride;
-    const uint32_t smask = (1u << A.log_s) - 1;
 
     // ---- load R rows x C columns (row r of column c lives at c + (n/R)*r)
     for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
@@ -117,84 +231,114 @@ __global__ void __launch_bounds__(256, 4) k_ntt_pass(const NttPassArgs A) {
         } else {
             v = Fr::zero();
         }
-        sts(idx, v);
+        tile.st(idx, v);
     }
     __syncthreads();
+    ntt_tile_stages<S>(A, tile, c0);
+    ntt_tile_store<S>(A, tile, c0, y);
+}
 
-    // ---- S radix-2 stages in shared memory (decimation in frequency, in place), two stages per round trip: a thread
-    // takes rows r0, r0+q, r0+2q, r0+3q (q = a quarter of the current block), does the two butterflies of stage i and
-    // the two of stage i+1 in registers (4 twiddle products, as two radix-2 stages would) and writes the 4 rows back:
-    // half the shared-memory traffic and barriers of the plain radix-2 loop.
-    uint32_t i = 0;
-#pragma unroll 1
-    for (; i + 1 < S; i += 2) {
-        const uint32_t log_q = S - 2 - i, q = 1u << log_q;
-        for (uint32_t g = tid; g < ((R / 4) << log_c); g += T) {
-            const uint32_t c = g & cmask, gf = g >> log_c;
-            const uint32_t blk = gf >> log_q, rp = gf & (q - 1);
-            const uint32_t i0 = ((((blk << (log_q + 2)) + rp)) << log_c) + c, st = q << log_c;
-            const uint32_t base = ((c0 + c) >> A.log_s) << A.log_s;  // s * p'
-            const uint32_t ea = (base + (rp << log_cols)) << i;          // stage i, rows (r0, r0 + 2q)
-            const uint32_t eb = (base + ((rp + q) << log_cols)) << i;    // stage i, rows (r0 + q, r0 + 3q)
-            const uint32_t ec = ea << 1;                                 // stage i + 1, both pairs
-            const fe_t a0 = lds(i0), a1 = lds(i0 + st), a2 = lds(i0 + 2 * st), a3 = lds(i0 + 3 * st);
-            const fe_t u0 = Fr::add(a0, a2), u1 = Fr::add(a1, a3);
-            fe_t d0 = Fr::sub(a0, a2), d1 = Fr::sub(a1, a3);
-            if (ea) d0 = Fr::mul(d0, ld_fe_nc(A.tw + ea));
-            // zero-padded first pass (coeff_to_extended: 3/4 of the rows are zero): a1 = a3 = 0 in the first round, 0 * w = 0
-            if (!Fr::is_zero(d1)) d1 = Fr::mul(d1, ld_fe_nc(A.tw + eb));
-            const fe_t wc = ld_fe_nc(A.tw + ec);
-            sts(i0, Fr::add(u0, u1));
-            sts(i0 + 2 * st, Fr::add(d0, d1));
-            fe_t v1 = Fr::sub(u0, u1), v3 = Fr::sub(d0, d1);
-            if (ec) {
-                v1 = Fr::mul(v1, wc);
-                v3 = Fr::mul(v3, wc);
+// ---- the same pass with the tile loads done by the TMA engine ----------------------------------------------------------
+// Persistent CTAs (grid = resident CTAs) walk the (vector, column tile) list; the R x C tile of the NEXT work item is
+// fetched by ONE cp.async.bulk.tensor (a 5-D tensor map over [outer vector][inner vector][row][128-byte line][word],
+// 128-byte swizzle) into the other half of a two-stage shared-memory ring and completes on that stage's mbarrier while
+// the 256 threads run the butterflies of the current tile: the compute warps issue no global loads for the tile and
+// never wait for them.  Rows beyond in_len (the zero padding of coeff_to_extended) lie outside the tensor and are
+// zero-filled by the copy engine without touching memory.
+struct NttTmaArgs {
+    uint32_t tiles_per_vec;  // n / R / C
+    uint32_t total_tiles;    // tiles_per_vec * batch
+    uint32_t inner;          // vectors per outer group (tensor dims 3 / 4)
+    uint32_t tile_bytes;
+};
+__device__ __forceinline__ uint32_t ntt_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ntt_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+template <int S>
+__global__ void __launch_bounds__(256, 3) k_ntt_pass_tma(const NttPassArgs A, const NttTmaArgs M, const __grid_constant__ CUtensorMap tmap) {
+    constexpr uint32_t R = 1u << S;
+    extern __shared__ uint4 smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2];
+    // the swizzle pattern is a function of the shared-memory address: align the ring to 1024 bytes
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t tid = threadIdx.x, log_c = A.log_c, cmask = (1u << log_c) - 1;
+    const uint32_t log_cols = A.log_n - S;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ntt_smem_addr(&bars[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ntt_smem_addr(&bars[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint32_t work, uint32_t stage) {   // thread 0 only
+        const uint32_t vec = work / M.tiles_per_vec, tilei = work % M.tiles_per_vec;
+        const uint32_t bar = ntt_smem_addr(&bars[stage]), dst = ntt_smem_addr(ring + (size_t)stage * M.tile_bytes);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of this stage before the async write
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(M.tile_bytes) : "memory");
+        // coordinates: word in line, line = first column of the tile / 4, row, inner vector, outer vector
+        asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+                     "l"(&tmap), "r"(bar), "r"(0), "r"((int)((tilei << log_c) >> 2)), "r"(0), "r"((int)(vec % M.inner)), "r"((int)(vec / M.inner))
+                     : "memory");
+    };
+    uint32_t work = blockIdx.x, k = 0;
+    if (tid == 0 && work < M.total_tiles) issue(work, 0);
+    for (; work < M.total_tiles; work += gridDim.x, k++) {
+        const uint32_t stage = k & 1u;
+        const uint32_t next = work + gridDim.x;
+        if (tid == 0 && next < M.total_tiles) issue(next, stage ^ 1u);
+        ntt_mbar_wait(ntt_smem_addr(&bars[stage]), (k >> 1) & 1u);
+        SwizzledTile tile;
+        tile.base = reinterpret_cast<uint4*>(ring + (size_t)stage * M.tile_bytes);
+        const uint32_t vec = work / M.tiles_per_vec, c0 = (work % M.tiles_per_vec) << log_c;
+        fe_t* y = A.y + (uint64_t)vec * A.out_stride;
+        if (A.pre) {   // coset twist of the coefficients: element gi times pre3[gi % 3] (the rows past in_len are zero)
+            const uint32_t live = min((uint32_t)R, (A.in_len + (1u << log_cols) - 1) >> log_cols) << log_c;
+            for (uint32_t idx = tid; idx < live; idx += blockDim.x) {
+                const uint32_t r = idx >> log_c, c = idx & cmask;
+                const uint32_t m3 = (c0 + c + (r << log_cols)) % 3u;
+                if (m3) tile.st(idx, Fr::mul(tile.ld(idx), A.pre3[m3]));
             }
-            sts(i0 + st, v1);
-            sts(i0 + 3 * st, v3);
+            __syncthreads();
         }
-        __syncthreads();
-    }
-    if (i < S) {  // odd S: one radix-2 stage left (half = 1)
-        for (uint32_t b = tid; b < ((R / 2) << log_c); b += T) {
-            const uint32_t c = b & cmask, bf = b >> log_c;
-            const uint32_t i0 = ((bf << 1) << log_c) + c, i1 = i0 + (1u << log_c);
-            const uint32_t e = (((c0 + c) >> A.log_s) << A.log_s) << i;
-            const fe_t a = lds(i0), bb = lds(i1);
-            fe_t d = Fr::sub(a, bb);
-            if (e) d = Fr::mul(d, ld_fe_nc(A.tw + e));
-            sts(i0, Fr::add(a, bb));
-            sts(i1, d);
-        }
-        __syncthreads();
-    }
-
-    // ---- store: local row r holds output digit t = bitrev_S(r)
-    if (A.log_s == 0) {
-        // first pass: out index = R*col + t, make t the fastest index for contiguous stores
-        for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
-            uint32_t t = idx & (R - 1), c = idx >> S;
-            uint32_t r = __brev(t) >> (32 - S);
-            fe_t v = lds((r << log_c) + c);
-            uint32_t oi = ((c0 + c) << S) + t;
-            if (A.post) v = Fr::mul(v, A.post3[oi % 3u]);
-            st_fe(y + oi, v);
-        }
-    } else {
-        for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
-            uint32_t r = idx >> log_c, c = idx & cmask;
-            uint32_t t = __brev(r) >> (32 - S);
-            uint32_t col = c0 + c, q = col & smask, pp = col >> A.log_s;
-            uint32_t oi = q + (pp << (A.log_s + S)) + (t << A.log_s);
-            fe_t v = lds(idx);
-            if (A.post) v = Fr::mul(v, A.post3[oi % 3u]);
-            st_fe(y + oi, v);
-        }
+        ntt_tile_stages<S>(A, tile, c0);
+        ntt_tile_store<S>(A, tile, c0, y);
+        __syncthreads();   // every thread is done with this stage before thread 0 hands it back to the copy engine
     }
 }
 
 typedef void (*ntt_kernel_t)(const NttPassArgs);
+typedef void (*ntt_tma_kernel_t)(const NttPassArgs, const NttTmaArgs, const CUtensorMap);
+static ntt_tma_kernel_t pass_kernel_tma(int S) {
+    switch (S) {
+        case 4: return k_ntt_pass_tma<4>;
+        case 5: return k_ntt_pass_tma<5>;
+        case 6: return k_ntt_pass_tma<6>;
+        case 7: return k_ntt_pass_tma<7>;
+        case 8: return k_ntt_pass_tma<8>;
+        default: return nullptr;
+    }
+}
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+    static encode_tiled_fn fn = []() -> encode_tiled_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return (encode_tiled_fn)p;
+    }();
+    return fn;
+}
 static ntt_kernel_t pass_kernel(int S) {
     switch (S) {
         case 1: return k_ntt_pass<1>;
@@ -356,10 +500,52 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         size_t smem = ((size_t)sizeof(fe_t) << S[p]) << log_c;
         ntt_kernel_t kern = pass_kernel(S[p]);
         if (smem > 48 * 1024) B2R_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(1u << (log_cols - log_c), (unsigned)batch);
-        { KTimer kt(ctx, "ntt_pass", (double)batch * n);
-        kern<<<grid, 256, smem, ctx->stream>>>(A); }
-        B2R_LAUNCH_CHECK(ctx);
+        // TMA path: tiles of at most 32 KiB (two ring stages, 3 CTAs per SM), at least one 128-byte line per row, rows <= 256
+        bool use_tma = false;
+        {
+            // opt-in ("1"): measured on B200 the plain-load kernel is faster (4 CTAs/SM already hide the tile loads behind
+            // other CTAs' butterflies; the two-stage ring costs a CTA of occupancy) - profiles/r02_tma_experiments.md
+            const char* ov = getenv("B2R_NTT_TMA");
+            const bool want = ov && ov[0] == '1';
+            const uint32_t ncols = 1u << log_cols;
+            const uint32_t vec_rows = (uint32_t)((src_len + ncols - 1) / ncols);   // rows that exist in memory (rest: zero fill)
+            use_tma = want && get_encode_tiled() && pass_kernel_tma(S[p]) && log_c >= 2 && smem <= 32 * 1024 && vec_rows >= 1 &&
+                      (src_len % ncols == 0) && (src_stride % 4 == 0) && ((uintptr_t)src % 16 == 0);
+            if (use_tma) {
+                const uint32_t inner = A.in_inner ? A.in_inner : (uint32_t)batch, outer = A.in_inner ? (uint32_t)(batch / A.in_inner) : 1u;
+                const uint64_t inner_stride = src_stride, outer_stride = A.in_inner ? A.in_stride2 : src_stride * batch;
+                CUtensorMap tmap;
+                const cuuint64_t gdim[5] = {32, ncols / 4, vec_rows, inner, outer};
+                const cuuint64_t gstr[4] = {128, (cuuint64_t)ncols * 32, inner_stride * 32, (outer > 1 ? outer_stride : inner_stride * inner) * 32};
+                const cuuint32_t box[5] = {32, 1u << (log_c - 2), 1u << S[p], 1, 1};
+                const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                CUresult cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, (void*)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (cr != CUDA_SUCCESS) {
+                    use_tma = false;   // shapes the encoder refuses go through the plain kernel
+                } else {
+                    NttTmaArgs M;
+                    M.tiles_per_vec = 1u << (log_cols - log_c);
+                    M.total_tiles = M.tiles_per_vec * (uint32_t)batch;
+                    M.inner = inner;
+                    M.tile_bytes = (uint32_t)smem;
+                    const size_t dyn = 2 * smem + 1024;
+                    ntt_tma_kernel_t tk = pass_kernel_tma(S[p]);
+                    B2R_CUDA(ctx, cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                    const uint32_t resident = 3u * (uint32_t)ctx->sm_count;
+                    const uint32_t gridx = M.total_tiles < resident ? M.total_tiles : resident;
+                    { KTimer kt(ctx, "ntt_pass", (double)batch * n);
+                    tk<<<gridx, 256, dyn, ctx->stream>>>(A, M, tmap); }
+                    B2R_LAUNCH_CHECK(ctx);
+                }
+            }
+        }
+        if (!use_tma) {
+            dim3 grid(1u << (log_cols - log_c), (unsigned)batch);
+            { KTimer kt(ctx, "ntt_pass", (double)batch * n);
+            kern<<<grid, 256, smem, ctx->stream>>>(A); }
+            B2R_LAUNCH_CHECK(ctx);
+        }
         if (last && dst != out) {
             B2R_CUDA(ctx, cudaMemcpy2DAsync(out, out_stride * 32, dst, dst_stride * 32, n * 32, batch, cudaMemcpyDeviceToDevice, ctx->stream));
         }

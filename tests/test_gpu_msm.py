@@ -170,3 +170,26 @@ def test_msm_2p20_config5(ctx):
         assert got[j] == want, f"vector {j} vs closed form"
         assert np.array_equal(CO.best_multiexp(arr[j], bases), outs[0][j]), f"vector {j} vs CPU best_multiexp"
     bs.free()
+
+
+@pytest.mark.parametrize("variant", ["3", "4"])
+def test_accumulate_ring_variants_same_result(ctx, monkeypatch, variant):
+    """the opt-in accumulation kernels that stage the table points through a shared-memory ring (msm.cu
+    k_accum_entries_ring: 3 = per-lane cp.async.bulk + mbarrier, 4 = LDGSTS groups): identical commitments for a dense
+    vector, a sparse one and a ragged length"""
+    import cpu_oracle as CO
+    from util import random_fr_np
+    n = (1 << 15) + 77
+    bases = CO.g1_multiples(n)
+    bs = ctx.bases_register(bases)
+    dense = random_fr_np(n, 41)
+    sparse = dense.copy()
+    sparse[np.random.default_rng(2).random(n) < 0.9] = 0
+    arr = np.stack([dense, sparse])
+    monkeypatch.setenv("B2R_MSM_VARIANT", "0")
+    want = ctx.msm_batch(bs, arr)
+    monkeypatch.setenv("B2R_MSM_VARIANT", variant)
+    got = ctx.msm_batch(bs, arr)
+    assert np.array_equal(got, want)
+    assert np.array_equal(CO.best_multiexp(dense, bases), want[0])
+    bs.free()

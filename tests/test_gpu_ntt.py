@@ -111,3 +111,38 @@ def test_full_size_full_array_vs_cpu_oracle(ctx, log_n):
         ext = ctx.coset_ntt(co, log_n, log_n + 2)
         assert np.array_equal(ext, CO.coeff_to_extended(co, log_n, log_n + 2))
         assert np.array_equal(ctx.coset_intt(ext, log_n + 2), CO.extended_to_coeff(ext, log_n + 2))
+
+
+@pytest.mark.parametrize("log_n,batch", [(13, 3), (17, 2), (19, 1), (22, 1)])
+def test_tma_tile_loader_matches_plain_loads(ctx, monkeypatch, log_n, batch):
+    """the opt-in pass kernel whose tiles are fetched by cp.async.bulk.tensor + mbarrier (ntt.cu k_ntt_pass_tma,
+    B2R_NTT_TMA=1): same outputs, bit for bit, as the default kernel - forward, inverse, and the zero-padded coset
+    extension (rows beyond the coefficients are zero-filled by the copy engine)"""
+    import torch
+    n = 1 << log_n
+    a = random_fr_np(n * batch, 3000 + log_n)
+    w = fr_to_np([O.omega_for(log_n)])[0]
+
+    def run():
+        t = torch.from_numpy(a.view(np.int64)).cuda()
+        ctx.ntt_batch_dev(t.data_ptr(), batch, w, log_n)
+        ctx.sync()
+        fwd = t.cpu().numpy().copy()
+        ctx.intt_batch_dev(t.data_ptr(), batch, log_n)
+        ctx.sync()
+        inv = t.cpu().numpy().copy()
+        ext = None
+        if log_n <= 19:
+            e = torch.zeros(batch * 4 * n * 4, dtype=torch.int64, device="cuda")
+            ctx.coset_ntt_batch_dev(t.data_ptr(), batch, log_n, log_n + 2, e.data_ptr())
+            ctx.sync()
+            ext = e.cpu().numpy().copy()
+        return fwd, inv, ext
+
+    monkeypatch.setenv("B2R_NTT_TMA", "0")
+    base = run()
+    monkeypatch.setenv("B2R_NTT_TMA", "1")
+    tma = run()
+    for x, y in zip(base, tma):
+        assert (x is None and y is None) or np.array_equal(x, y)
+    assert np.array_equal(base[1].view(np.uint64).reshape(-1, 4), a)     # the inverse undoes the forward transform

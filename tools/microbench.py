@@ -26,7 +26,8 @@ def timeit(fn, iters=5, warm=2):
 def random_bases(n, seed=1):
     """n pseudo-random distinct points: (a_i)G is slow in python; use multiples via C-free trick:
     take P_i = (i+1)G (running add, batch normalise) - fine for timing and closed-form checks."""
-    return O.g1_multiples(n)
+    import cpu_oracle as CO
+    return CO.g1_multiples(n)
 
 
 def main():
@@ -54,13 +55,19 @@ def main():
     for L in a.msm:
         n = 1 << L
         t0 = time.time(); pts = random_bases(n); t1 = time.time()
-        bs = ctx.bases_register(g1_to_np(pts)); t2 = time.time()
+        bs = ctx.bases_register(pts); t2 = time.time()
         print(f"msm 2^{L}: bases gen {t1-t0:.1f}s register {t2-t1:.2f}s", flush=True)
         sc = torch.from_numpy(random_fr_np(n, 0x5EED).view(np.int64)).cuda()
         out = torch.zeros(8 * a.batch, dtype=torch.int64, device="cuda")
         best, avg = timeit(lambda: ctx.msm_batch_dev(bs, sc.data_ptr(), 1, n, out.data_ptr(), uniform=True))
         gb = n * 96 / 1e9
         print(f"msm 2^{L} uniform: best {best:.3f} ms avg {avg:.3f} -> {gb/best*1e3:.1f} GB/s algorithmic", flush=True)
+        ctx.profile_enable(True); ctx.profile_dump(clear=True)
+        ctx.msm_batch_dev(bs, sc.data_ptr(), 1, n, out.data_ptr(), uniform=True)
+        print("   per kernel (ms):", {k: round(v[0], 3) for k, v in ctx.profile_dump(clear=True).items()}, flush=True)
+        ctx.profile_enable(False)
+        best, avg = timeit(lambda: ctx.msm_batch_dev(bs, sc.data_ptr(), 1, n, out.data_ptr(), uniform=False))
+        print(f"msm 2^{L} (no hint): best {best:.3f} ms avg {avg:.3f}", flush=True)
         if L <= 17:
             scb = torch.from_numpy(random_fr_np(n * a.batch, 7).view(np.int64)).cuda()
             best, avg = timeit(lambda: ctx.msm_batch_dev(bs, scb.data_ptr(), a.batch, n, out.data_ptr(), uniform=True))
