@@ -165,6 +165,34 @@ def test_two_contexts_interleaved(ctx, small):
     assert bytes(a3[0]) == bytes(a1[0]) and PL.verify_proof(opk, srs.s, bytes(a3[0]))
 
 
+def test_one_context_per_device_in_one_process(ctx, small):
+    """the multi-GPU shape a Rust host uses: one context per device in ONE process, calls
+    interleaved from one thread whose current device never changes.  Needs a 2-GPU lease (gpurun --gpus 2)."""
+    import torch
+    import b2rsa
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    bits, k, pk, srs, opk = small
+    torch.cuda.set_device(0)
+    other = b2rsa.Context(1)
+    prog1 = other.rsa_program(bits, k)
+    g1, gl1 = other.srs_setup(k, fr_to_np([O.srs_secret(k)])[0])
+    pk1 = other.rsa_keygen(prog1, g1, gl1)
+    assert torch.cuda.current_device() == 0            # the library restored the caller's device
+    nl, sl, hl = RF.batch(bits, 3, start=11)
+    a, sa = pk.prove_batch(nl, sl, hl, 21, nonce=7)     # device 0
+    b, sb = pk1.prove_batch(nl, sl, hl, 21, nonce=7)    # device 1
+    a2, _ = pk.prove_batch(nl[:1], sl[:1], hl[:1], 21, nonce=7)
+    assert sa.tolist() == sb.tolist() == [1, 1, 1]
+    assert a.tobytes() == b.tobytes() and bytes(a2[0]) == bytes(a[0])
+    assert _vk(pk)["fixed_commitments"] == _vk(pk1)["fixed_commitments"]
+    for i in range(3):
+        assert PL.verify_proof(opk, srs.s, bytes(b[i]))
+    pk1.free(); prog1.free(); g1.free(); gl1.free()
+    other.close()
+    assert torch.cuda.current_device() == 0
+
+
 def test_keygen_rejects_wrong_srs_size(ctx):
     """a Lagrange basis of another domain must not be accepted silently"""
     import b2rsa
