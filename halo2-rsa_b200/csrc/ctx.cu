@@ -65,7 +65,7 @@ int32_t b2r_ctx_create(int32_t device, b2r_ctx** out) {
         g_create_err = "device is not sm_100 (kernels are built for sm_100a only)";
         return B2R_ERR_NO_DEVICE;
     }
-    if (cudaSetDevice(device) != cudaSuccess) return B2R_ERR_CUDA;
+    b2r::DeviceGuard guard(device);   // the stream is created on `device`; the caller's current device is restored on return
     b2r_ctx* ctx = new (std::nothrow) b2r_ctx();
     if (!ctx) return B2R_ERR_NOMEM;
     ctx->device = device;
@@ -81,7 +81,7 @@ int32_t b2r_ctx_create(int32_t device, b2r_ctx** out) {
 
 int32_t b2r_ctx_destroy(b2r_ctx* ctx) {
     if (!ctx) return B2R_ERR_INVALID;
-    cudaSetDevice(ctx->device);
+    b2r::DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->twiddles) cudaFree(kv.second);
     for (auto& s : ctx->scratch)
