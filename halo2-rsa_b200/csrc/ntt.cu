@@ -421,8 +421,12 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
     const fe_t* tw = nullptr;
     B2R_TRY(ntt_get_twiddles(ctx, omega, log_n, &tw));
 
-    int npass = (log_n + 8) / 9;
-    int S[4];
+    // stages per pass: 9 (64 KiB tiles, fewest passes) for batches; a single short transform is a latency chain of a few
+    // hundred CTAs, where three passes of 32 KiB tiles at 4 CTAs/SM finish sooner than two of 64 KiB (2^17: 57 vs 72 us)
+    int max_s = (batch << log_n) <= ((size_t)1 << 18) ? 8 : 9;
+    if (const char* ov = getenv("B2R_NTT_MAXS")) max_s = atoi(ov) >= 4 && atoi(ov) <= 9 ? atoi(ov) : 9;   // tuning hook: stages per pass
+    int npass = (log_n + max_s - 1) / max_s;
+    int S[8];
     {
         int base = log_n / npass, extra = log_n % npass;
         for (int p = 0; p < npass; p++) S[p] = base + (p < extra ? 1 : 0);

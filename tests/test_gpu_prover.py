@@ -282,3 +282,42 @@ def test_prover_argument_errors(small):
     nl, sl, hl = RF.batch(bits, 1)
     with pytest.raises(b2rsa.B2RError):
         pk.prove_batch(nl, sl, hl, seed=0)
+
+
+def test_empty_batches_and_argument_errors(ctx, small):
+    """edge cases at the ABI: empty batches are no-ops that return OK, every misuse comes back as a status code with a
+    message (nothing aborts or throws across the boundary)"""
+    import ctypes as C
+    import b2rsa
+    bits, k, pk, srs, opk = small
+    lib, h = ctx.lib, ctx.h
+    nl, sl, hl = RF.batch(bits, 1)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    proofs = np.zeros(pk.proof_bytes, dtype=np.uint8)
+    status = np.full(1, 7, dtype=np.uint8)
+    key = (C.c_uint8 * 32)(*range(32))
+    # empty batch: OK, outputs untouched
+    assert lib.b2r_rsa_prove_batch(h, pk.h, p(nl), p(sl), p(hl), 0, 5, p(proofs), p(status)) == 0
+    assert lib.b2r_rsa_prove_batch_ex(h, pk.h, p(nl), p(sl), p(hl), 0, C.cast(key, C.c_void_p), 1, 0, p(proofs), p(status)) == 0
+    assert status[0] == 7 and not proofs.any()
+    adv = np.zeros((5, 1 << k, 4), dtype=np.uint64)
+    assert lib.b2r_rsa_witness_batch(h, pk.prog.h, p(nl), p(sl), p(hl), 0, 0, p(adv), p(status)) == 0
+    out = np.zeros(8, dtype=np.uint64)
+    g, gl = ctx.srs_setup(10, fr_to_np([O.srs_secret(10)])[0])
+    assert lib.b2r_msm_g1_batch(h, g.h, None, 0, 0, p(out)) == 0                       # m = 0
+    sc = np.zeros((1, 4), dtype=np.uint64)
+    assert lib.b2r_msm_g1_batch(h, g.h, p(sc), 1, 0, p(out)) == 0 and not out.any()    # n = 0: the identity
+    # misuse
+    assert lib.b2r_rsa_prove_batch_ex(h, pk.h, p(nl), p(sl), p(hl), 1, None, 1, 0, p(proofs), p(status)) == b2rsa.ERR_INVALID
+    assert b"seed" in lib.b2r_last_error(h)
+    assert lib.b2r_rsa_prove_batch_ex(h, pk.h, p(nl), p(sl), p(hl), 1, C.cast(key, C.c_void_p), 1, 64, p(proofs), p(status)) == b2rsa.ERR_INVALID
+    zero = (C.c_uint8 * 32)()
+    assert lib.b2r_rsa_prove_batch_ex(h, pk.h, p(nl), p(sl), p(hl), 1, C.cast(zero, C.c_void_p), 1, 2, p(proofs), p(status)) == b2rsa.ERR_INVALID
+    assert lib.b2r_rsa_prove_batch(h, None, p(nl), p(sl), p(hl), 1, 5, p(proofs), p(status)) == b2rsa.ERR_INVALID
+    assert lib.b2r_rsa_prove_batch(None, pk.h, p(nl), p(sl), p(hl), 1, 5, p(proofs), p(status)) == b2rsa.ERR_INVALID
+    assert lib.b2r_msm_g1_batch(h, g.h, p(sc), 1, 1 << 11, p(out)) == b2rsa.ERR_INVALID   # more scalars than bases
+    assert lib.b2r_pk_set_transcript_repr(None, p(sc)) == b2rsa.ERR_INVALID
+    # a 32-byte all-zero KEY is a legitimate key (only the 64-bit seed form rejects zero)
+    assert lib.b2r_rsa_prove_batch_ex(h, pk.h, p(nl), p(sl), p(hl), 1, C.cast(zero, C.c_void_p), 1, 0, p(proofs), p(status)) == 0
+    assert status[0] == 1 and PL.verify_proof(opk, srs.s, proofs.tobytes())
+    g.free(); gl.free()
