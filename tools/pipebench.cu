@@ -8,6 +8,7 @@
 #include <cstring>
 #include "experiments/ec29.cuh"
 #include "experiments/field_f64.cuh"
+#include "experiments/field_kara.cuh"
 
 using namespace b2r;
 
@@ -210,6 +211,22 @@ __global__ void k_f64mul(fe_t* out, const fe_t* in, int iters) {
     out[t] = r;
 }
 
+template <int ILP>
+__global__ void k_karamul(fe_t* out, const fe_t* in, int iters) {
+    fe_t x[ILP], y;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    y = in[t & 1023];
+    for (int j = 0; j < ILP; j++) x[j] = in[(t + j + 1) & 1023];
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++) x[j] = FqKara::mul(x[j], y);
+    }
+    fe_t r = x[0];
+    for (int j = 1; j < ILP; j++) r = Fq::add(r, x[j]);
+    out[t] = r;
+}
+
 template <class F>
 static double time_ms(F launch, int reps = 5) {
     cudaEvent_t s, e;
@@ -244,6 +261,47 @@ int main(int argc, char** argv) {
     void* buf;
     CK(cudaMalloc(&buf, (size_t)sms * 16 * 1024 * 32));
     CK(cudaMemset(buf, 0x11, (size_t)sms * 16 * 1024 * 32));
+    if (argc > 1 && !strcmp(argv[1], "kara")) {
+        fe_t* in0 = (fe_t*)buf;
+        // valid field elements: clear the top bits of every element of the input block
+        {
+            fe_t* h = (fe_t*)malloc(1024 * 32 * 2);
+            uint64_t st = 88172645463325252ull;
+            for (int i = 0; i < 2048; i++) {
+                for (int k = 0; k < 8; k++) { st ^= st << 13; st ^= st >> 7; st ^= st << 17; h[i].l[k] = (uint32_t)(st >> 11); }
+                h[i].l[7] &= 0x0fffffffu;
+            }
+            CK(cudaMemcpy(in0, h, 2048 * 32, cudaMemcpyHostToDevice));
+            free(h);
+        }
+        fe_t* o1 = in0 + 4096;
+        const int grid0 = sms * 8;
+        fe_t* o2 = o1 + (size_t)grid0 * 256;
+        k_fqmul<1><<<grid0, 256>>>(o1, in0, 64);
+        k_karamul<1><<<grid0, 256>>>(o2, in0, 64);
+        CK(cudaDeviceSynchronize());
+        const size_t cnt = (size_t)grid0 * 256;
+        fe_t* h1 = (fe_t*)malloc(cnt * 32);
+        fe_t* h2 = (fe_t*)malloc(cnt * 32);
+        CK(cudaMemcpy(h1, o1, cnt * 32, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h2, o2, cnt * 32, cudaMemcpyDeviceToHost));
+        size_t bad = 0;
+        for (size_t i = 0; i < cnt; i++) bad += memcmp(&h1[i], &h2[i], 32) != 0;
+        printf("Karatsuba mul parity vs Fq::mul: %zu mismatches of %zu (64 chained products each)\n", bad, cnt);
+        for (int cps : {2, 4, 8}) {
+            for (int th : {128, 256}) {
+                const int grid = sms * cps;
+                const double m = (double)grid * th * 512;
+                double tb1 = time_ms([&] { k_fqmul<1><<<grid, th>>>(o1, in0, 512); });
+                double tb2 = time_ms([&] { k_fqmul<2><<<grid, th>>>(o1, in0, 512); });
+                double t1 = time_ms([&] { k_karamul<1><<<grid, th>>>(o1, in0, 512); });
+                double t2 = time_ms([&] { k_karamul<2><<<grid, th>>>(o1, in0, 512); });
+                printf("warps/SM %2d  Fq::mul ILP1 %6.1f ILP2 %6.1f   Karatsuba ILP1 %6.1f ILP2 %6.1f  Gmul/s\n", cps * th / 32, m / tb1 / 1e6, 2 * m / tb2 / 1e6,
+                       m / t1 / 1e6, 2 * m / t2 / 1e6);
+            }
+        }
+        return 0;
+    }
     if (argc > 1) {
         // profiling mode (ncu): one launch of each kernel of interest at full occupancy
         fe_t* in0 = (fe_t*)buf;
