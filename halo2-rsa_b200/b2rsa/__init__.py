@@ -68,6 +68,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_rsa_commit_batch_dev": [vp, vp, vp, vp, vp, vp, sz, u64, u32, u32, vp, vp, vp, vp],
         "b2r_rsa_program_build": [vp, u32, vp, sz, u32, C.POINTER(vp)],
         "b2r_rsa_program_build_var": [vp, u32, u32, u32, C.POINTER(vp)],
+        "b2r_rsa_program_build_sha_tail": [vp, u32, vp, sz, u32, C.POINTER(vp)],
         "b2r_bigint_program_build": [vp, u32, u32, u32, u32, C.POINTER(vp)],
         "b2r_prog_aux_words": [vp],
         "b2r_prog_free": [vp, vp],
@@ -299,6 +300,13 @@ class Context:
         """pkcs1v15 circuit with RSAPubE::Var: third input array = hash limbs then the exponent word"""
         h = C.c_void_p()
         self._ck(self.lib.b2r_rsa_program_build_var(self.h, bits_len, exp_limb_bits, k, C.byref(h)))
+        return RsaProgram(self, h, bits_len, k)
+
+    def rsa_program_sha_tail(self, bits_len: int, k: int, e: int = 65537) -> "RsaProgram":
+        """RSASignatureVerifier's digest-byte composition + verification (reference src/lib.rs:183-248)"""
+        e_le = np.frombuffer(e.to_bytes((e.bit_length() + 7) // 8, "little"), dtype=np.uint8).copy()
+        h = C.c_void_p()
+        self._ck(self.lib.b2r_rsa_program_build_sha_tail(self.h, bits_len, _host_ptr(e_le), e_le.size, k, C.byref(h)))
         return RsaProgram(self, h, bits_len, k)
 
     BIGINT_OPS = {"refresh": 6, "add_mod": 7, "sub_mod": 8, "pow_mod": 9, "is_zero": 10, "is_equal_fresh": 11, "is_less_than": 12,

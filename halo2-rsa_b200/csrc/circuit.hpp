@@ -1052,6 +1052,41 @@ inline AssignedValue record_rsa_pkcs1v15(RegionCtx& rc, unsigned bits_len, const
 
 // pkcs1v15 circuit with RSAPubE::Var (src/chip.rs:372-390 test_rsa_signature_with_hash_circuit's shape): the exponent is an
 // assigned one-limb integer of which `exp_limb_bits` bits are used.  Inputs: n limbs, signature limbs, hash limbs, then e.
+// RSASignatureVerifier::verify_pkcs1v15_signature (src/lib.rs:183-248), the part the reference itself holds: the 32
+// digest bytes that halo2-dynamic-sha256's chip hands over as assigned cells (`decompose_digest_to_bytes`, reversed:
+// src/lib.rs:210-213) are composed into four 64-bit limbs - per limb `assign_constant(0)`, then for each of its 8 bytes
+// `assign_constant(2^(8 j))` and `mul_add(coeff, byte, limb)` (src/lib.rs:222-236) - and the integer goes to
+// RSAChip::verify_pkcs1v15_signature in the same region.  The SHA-256 compression itself lives in the external crate
+// (unpinned, not vendored: DESIGN.md section 7); its output cells are stood in for by 32 `assign_value` rows in a region
+// of their own, so everything from the byte cells on is the reference's layout.  No assert_one: the verifier returns
+// is_valid to its caller (src/lib.rs:245).
+inline AssignedValue record_rsa_verifier_from_digest(RegionCtx& rc, unsigned bits_len, const std::vector<uint8_t>& e_le) {
+    const unsigned nl = bits_len / 64;
+    configure_range_tags(rc, nl);
+    RSAChip rsa_chip(bits_len, 5);
+    MainGate main_gate;
+    UnassignedInteger sig_u, n_u;
+    for (unsigned i = 0; i < nl; i++) n_u.limbs.push_back(rc.input(i));
+    for (unsigned i = 0; i < nl; i++) sig_u.limbs.push_back(rc.input(nl + i));
+    AssignedRSASignature sign = rsa_chip.assign_signature(rc, sig_u);
+    AssignedRSAPublicKey public_key = rsa_chip.assign_public_key(rc, n_u, e_le);
+    // stand-in for the SHA chip's digest-byte cells: hashed_bytes[8 i + j] = byte j of limb i (least significant first)
+    std::vector<AssignedValue> hashed_bytes;
+    for (unsigned i = 0; i < 4; i++)
+        for (unsigned j = 0; j < 8; j++) hashed_bytes.push_back(main_gate.assign_value(rc, rc.op1(OP_SUBLIMB, rc.input(2 * nl + i), 8 * j, 8)));
+    // region "verify pkcs1v15 signature" (src/lib.rs:217-243)
+    AssignedInteger hashed_msg;
+    for (unsigned i = 0; i < 4; i++) {
+        AssignedValue limb_val = main_gate.assign_constant(rc, U256(0));
+        for (unsigned j = 0; j < 8; j++) {
+            AssignedValue coeff = main_gate.assign_constant(rc, U256::pow2(8 * j));
+            limb_val = main_gate.mul_add(rc, coeff, hashed_bytes[8 * i + j], limb_val);
+        }
+        hashed_msg.limbs.push_back(limb_val);
+    }
+    return rsa_chip.verify_pkcs1v15_signature(rc, public_key, hashed_msg, sign);
+}
+
 inline AssignedValue record_rsa_pkcs1v15_var(RegionCtx& rc, unsigned bits_len, unsigned exp_limb_bits) {
     const unsigned nl = bits_len / 64;
     configure_range_tags(rc, nl);

@@ -670,6 +670,17 @@ int32_t b2r_rsa_program_build(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_
     return build_program(ctx, bits_len, k, 4, [&](RegionCtx& rc) { return record_rsa_pkcs1v15(rc, bits_len, e); }, out);
 } B2R_ABI_CATCH(ctx)
 
+int32_t b2r_rsa_program_build_sha_tail(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_le, size_t e_len, uint32_t k, b2r_prog** out) try {
+    B2R_ENTER(ctx);
+    if (!out || !e_le || e_len == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build_sha_tail: null argument");
+    *out = nullptr;
+    bool e_nonzero = false;
+    for (size_t i = 0; i < e_len; i++) e_nonzero |= e_le[i] != 0;
+    if (!e_nonzero) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build_sha_tail: exponent is zero");
+    std::vector<uint8_t> e(e_le, e_le + e_len);
+    return build_program(ctx, bits_len, k, 4, [&](RegionCtx& rc) { return record_rsa_verifier_from_digest(rc, bits_len, e); }, out);
+} B2R_ABI_CATCH(ctx)
+
 int32_t b2r_rsa_program_build_var(b2r_ctx* ctx, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out) try {
     B2R_ENTER(ctx);
     if (!out) return fail(ctx, B2R_ERR_INVALID, "rsa_program_build_var: null argument");

@@ -154,6 +154,14 @@ int32_t b2r_prog_aux_words(const b2r_prog* prog);
  * (src/big_integer/chip.rs:664-696: one mul_mod, num_limbs selects and one square_mod per bit).  Input arrays as for
  * b2r_rsa_program_build with the third one holding hash[0..3], e per instance. */
 int32_t b2r_rsa_program_build_var(b2r_ctx* ctx, uint32_t bits_len, uint32_t exp_limb_bits, uint32_t k, b2r_prog** out);
+/* RSASignatureVerifier::verify_pkcs1v15_signature (reference src/lib.rs:183-248) from the digest bytes on - the part of
+ * the SHA-256 front end that the reference itself holds: the 32 digest-byte cells (which halo2-dynamic-sha256's chip, an
+ * unpinned external crate, would provide; stood in for by one assign_value row each) are composed into four 64-bit limbs
+ * by assign_constant / mul_add (src/lib.rs:222-236) and verified in the same region; is_valid is returned, not asserted
+ * (src/lib.rs:245).  Inputs as for b2r_rsa_program_build (the third array holds the digest as four little-endian
+ * 64-bit limbs, i.e. the 32 bytes least significant first). */
+int32_t b2r_rsa_program_build_sha_tail(b2r_ctx* ctx, uint32_t bits_len, const uint8_t* e_le, size_t e_len, uint32_t k,
+                                       b2r_prog** out);
 /* One BigIntInstructions method as the reference's in-file unit-test circuits drive it (src/big_integer/chip.rs:
  * 1861-1899 refresh, 1948-1986 add_mod, 2027-2070 sub_mod, 2229-2271 pow_mod), for the methods the pkcs1v15 circuit
  * does not call.  op: 6 = mul + refresh (both operand orders, assert_equal_fresh), 7 = add_mod, 8 = sub_mod,

@@ -124,6 +124,17 @@ class RsaTable:
         return int(lib().orc_rsa_synthesize(self.h, C.c_int(self.bits_len), _p(e_le), C.c_int(e_le.size),
                                             _p(n_limbs), _p(sig_limbs), _p(hash_limbs)))
 
+    def synthesize_digest(self, n_limbs, sig_limbs, hash_limbs, e: int = 65537) -> int:
+        """RSASignatureVerifier::verify_pkcs1v15_signature from the digest bytes on (reference src/lib.rs:183-248);
+        hash_limbs: the digest as four little-endian 64-bit limbs (their bytes are the 32 byte cells)"""
+        e_le = np.frombuffer(e.to_bytes((e.bit_length() + 7) // 8, "little"), dtype=np.uint8).copy()
+        n_limbs = np.ascontiguousarray(n_limbs, dtype=np.uint64)
+        sig_limbs = np.ascontiguousarray(sig_limbs, dtype=np.uint64)
+        digest_le = np.frombuffer(np.ascontiguousarray(hash_limbs, dtype="<u8").tobytes(), dtype=np.uint8).copy()
+        assert digest_le.size == 32
+        return int(lib().orc_rsa_synthesize_digest(self.h, C.c_int(self.bits_len), _p(e_le), C.c_int(e_le.size),
+                                                   _p(n_limbs), _p(sig_limbs), _p(digest_le)))
+
     def synthesize_var(self, n_limbs, sig_limbs, hash_limbs, e: int, exp_limb_bits: int) -> int:
         """the same circuit with RSAPubE::Var: e is an assigned one-limb integer, exp_limb_bits of its bits are used"""
         n_limbs = np.ascontiguousarray(n_limbs, dtype=np.uint64)

@@ -791,6 +791,38 @@ int orc_rsa_synthesize(orc_table* t, int bits_len, const uint8_t* e_le, int e_le
     return fe_eq(&is_valid.v, &FR.one) ? 1 : 0;
 }
 
+/* RSASignatureVerifier::verify_pkcs1v15_signature (src/lib.rs:183-248) from the digest bytes on: the 32 byte cells the
+ * external SHA-256 chip returns (stood in for by one assign_value row each, in the order of `hashed_bytes` after the
+ * reverse at src/lib.rs:213, i.e. least significant byte first), composed into four limbs by assign_constant / mul_add
+ * (src/lib.rs:222-236), then RSAChip::verify_pkcs1v15_signature in the same region.  digest_le: the 32 bytes, least
+ * significant first (= the 4 hash limbs of orc_rsa_synthesize as little-endian bytes).  Returns is_valid, -1 on panic. */
+int orc_rsa_synthesize_digest(orc_table* t, int bits_len, const uint8_t* e_le, int e_len, const uint64_t* n_limbs,
+                              const uint64_t* sig_limbs, const uint8_t* digest_le) {
+    rctx* c = &t->c;
+    bigchip ch = {64, bits_len / 64};
+    int nl = bits_len / 64;
+    fe tmp[MAXL];
+    bint sig, n, hashed;
+    for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(sig_limbs[i]);
+    bi_assign_integer(c, &ch, tmp, nl, &sig);
+    for (int i = 0; i < nl; i++) tmp[i] = fe_of_u64(n_limbs[i]);
+    bi_assign_integer(c, &ch, tmp, nl, &n);
+    aval bytes[32];
+    for (int i = 0; i < 32; i++) bytes[i] = mg_assign_value(c, fe_of_u64(digest_le[i]));
+    hashed.n = 4;
+    for (int i = 0; i < 4; i++) {
+        aval limb = mg_assign_constant(c, fe_zero());
+        for (int j = 0; j < 8; j++) {
+            aval coeff = mg_assign_constant(c, fe_of_u64((uint64_t)1 << (8 * j)));
+            limb = mg_mul_add(c, &coeff, &bytes[8 * i + j], &limb);
+        }
+        hashed.l[i] = limb;
+    }
+    aval is_valid = rsa_verify_pkcs1v15(c, &ch, bits_len, e_le, e_len, &n, &hashed, &sig);
+    if (c->failed) return -1;
+    return fe_eq(&is_valid.v, &FR.one) ? 1 : 0;
+}
+
 /* the same circuit with RSAPubE::Var (src/chip.rs:58-70, :99-114): the exponent is an assigned one-limb integer,
  * pow_mod walks exp_limb_bits of its bits.  Region order as above; e is assigned right after n. */
 int orc_rsa_synthesize_var(orc_table* t, int bits_len, int exp_limb_bits, uint64_t e_word, const uint64_t* n_limbs,

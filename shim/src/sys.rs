@@ -52,6 +52,7 @@ extern "C" {
     pub fn b2r_srs_setup(ctx: *mut b2r_ctx, k: u32, secret: *const Fr, g: *mut *mut b2r_bases, g_lagrange: *mut *mut b2r_bases) -> i32;
     // ---- Circuit::synthesize of the pkcs1v15 circuit (benches/bench.rs:132-225)
     pub fn b2r_rsa_program_build(ctx: *mut b2r_ctx, bits_len: u32, e_le: *const u8, e_len: usize, k: u32, out: *mut *mut b2r_prog) -> i32;
+    pub fn b2r_rsa_program_build_sha_tail(ctx: *mut b2r_ctx, bits_len: u32, e_le: *const u8, e_len: usize, k: u32, out: *mut *mut b2r_prog) -> i32;
     pub fn b2r_rsa_program_build_var(ctx: *mut b2r_ctx, bits_len: u32, exp_limb_bits: u32, k: u32, out: *mut *mut b2r_prog) -> i32;
     pub fn b2r_prog_free(ctx: *mut b2r_ctx, prog: *mut b2r_prog) -> i32;
     pub fn b2r_prog_info(prog: *const b2r_prog, rows_used: *mut u64, num_values: *mut u64, num_levels: *mut u64) -> i32;

@@ -24,7 +24,8 @@ int main(int argc, char** argv) {
     }
     unsigned bits = argc > 1 ? atoi(argv[1]) : 2048, k = argc > 2 ? atoi(argv[2]) : 17;
     const std::string mode = argc > 3 ? argv[3] : "65537";
-    unsigned long e = (mode == "var" || mode == "op") ? 0 : strtoul(argv[3], nullptr, 10);
+    // mode "digest" <e>: RSASignatureVerifier's byte composition + verify (src/lib.rs:183-248)
+    unsigned long e = (mode == "var" || mode == "op") ? 0 : mode == "digest" ? strtoul(argc > 4 ? argv[4] : "65537", nullptr, 10) : strtoul(argv[3], nullptr, 10);
     std::vector<uint8_t> e_le;
     for (unsigned long v = e; v; v >>= 8) e_le.push_back((uint8_t)v);
     try {
@@ -32,6 +33,7 @@ int main(int argc, char** argv) {
         AssignedValue is_valid;
         if (mode == "var") is_valid = record_rsa_pkcs1v15_var(rc, bits, argc > 4 ? atoi(argv[4]) : 17);
         else if (mode == "op") is_valid = record_bigint_op(rc, (uint32_t)atoi(argv[4]), bits, argc > 5 ? atoi(argv[5]) : 5, nullptr);
+        else if (mode == "digest") is_valid = record_rsa_verifier_from_digest(rc, bits, e_le);
         else is_valid = record_rsa_pkcs1v15(rc, bits, e_le);
         uint64_t hf = 0, hc = 0, hr = 0;
         for (uint32_t r = 0; r < rc.offset; r++) {

@@ -118,3 +118,24 @@ def test_rsa_var_witness_and_proof(ctx):
     assert PL.verify_proof(vk, O.srs_secret(k), bytes(proofs[0]))
     assert PL.verify_proof(vk, O.srs_secret(k), bytes(proofs[1]))
     pk.free(); g.free(); gl.free(); prog.free()
+
+
+def test_sha_tail_witness_matches_oracle(ctx):
+    """RSASignatureVerifier::verify_pkcs1v15_signature from the digest bytes on (reference src/lib.rs:183-248) on the GPU:
+    every advice cell equal to the oracle's table for valid signatures and for a corrupted digest (is_valid = 0)"""
+    import rsa_fixtures as RF
+    bits, k = 2048, 17
+    nl = bits // 64
+    prog = ctx.rsa_program_sha_tail(bits, k)
+    nls, sls, hls = RF.batch(bits, 3, start=20)
+    hls[2, 3] ^= np.uint64(1 << 7)
+    adv, valid = prog.witness_batch(nls, sls, hls)
+    assert valid.tolist() == [1, 1, 0]
+    for i in range(3):
+        t = CO.RsaTable(bits, k)
+        assert t.synthesize_digest(nls[i], sls[i], hls[i]) == int(valid[i])
+        assert t.check()[0] == 0
+        assert np.array_equal(t.advice(), adv[i]), f"instance {i}"
+        t.free()
+    assert prog.info()["rows_used"] < (1 << k) - 6
+    prog.free()

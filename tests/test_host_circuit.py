@@ -142,3 +142,34 @@ def test_refresh_aux_kat(exe):
     p = subprocess.run([exe, "aux", "64", "32", "32"], capture_output=True, text=True)
     inc = [int(x) for x in p.stdout.strip()[4:].split(",")]
     assert len(inc) == 64 and inc[0] == 1 and max(inc) == 2   # 2048-bit operands: every product limb spills 1-2 limbs
+
+
+@pytest.mark.parametrize("bits,k", [(1024, 15), (2048, 17)])
+def test_sha_tail_layout_equals_oracle_layout(exe, bits, k):
+    """RSASignatureVerifier::verify_pkcs1v15_signature from the digest bytes on (src/lib.rs:183-248: byte cells ->
+    assign_constant / mul_add composition into four limbs -> verify in the same region), recorder vs oracle; the oracle
+    table satisfies every gate / lookup / copy constraint and reports the same verdict as the bench circuit"""
+    p = subprocess.run([exe, str(bits), str(k), "digest", "65537"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout
+    d = dict(re.findall(r"(\w+)=(\S+)", p.stdout))
+    nl = bits // 64
+    n, s, h = RF.instance(bits, 2)
+    t = CO.RsaTable(bits, k)
+    assert t.synthesize_digest(RF.limbs64(n, nl), RF.limbs64(s, nl), RF.limbs64(h, 4)) == 1
+    assert t.check()[0] == 0
+    _assert_same_layout(d, _digest_of(t))
+    rows_tail = t.rows()
+    t.free()
+    # against the bench circuit: 4 range-checked limb assignments (2 rows each: 8 sublimbs, 4 per row) and the assert_one row are replaced by
+    # 32 byte cells + 4 x (1 + 2 x 8) composition rows
+    t2 = CO.RsaTable(bits, k)
+    assert t2.synthesize(RF.limbs64(n, nl), RF.limbs64(s, nl), RF.limbs64(h, 4)) == 1
+    assert rows_tail - t2.rows() == (32 + 4 * 17) - (4 * 2 + 1)
+    t2.free()
+    # a wrong digest byte -> is_valid = 0, constraints still satisfied (the verifier returns the bit, it does not assert it)
+    hb = RF.limbs64(h, 4).copy()
+    hb[1] ^= np.uint64(1 << 40)
+    t3 = CO.RsaTable(bits, k)
+    assert t3.synthesize_digest(RF.limbs64(n, nl), RF.limbs64(s, nl), hb) == 0
+    assert t3.check()[0] == 0
+    t3.free()
