@@ -195,7 +195,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Rust (no cargo/rustc in this image): timed arm is oracle/ - the C restatement of its CPU prover (rsa_witness.c + plonk_prover.c)",
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def config5_microbench(ctx, torch, stream):
@@ -429,7 +429,7 @@ def main():
             t = cpu_port_step(sample, threads)
             line["cpu_baseline"] = {"value": sample / t, "unit": "proofs/s", "cores": threads, "kind": "port",
                                     "sample": f"{sample} complete proofs of the same workload, one after the other: synthesize on 1 thread + the whole create_proof (oracle/plonk_prover.c) on {threads} threads ({t:.1f} s)"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
