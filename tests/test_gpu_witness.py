@@ -98,6 +98,30 @@ def test_other_key_sizes(ctx, bits, k):
     prog.free()
 
 
+@pytest.mark.parametrize("bits,k", [(768, 15), (3072, 18)])
+def test_limb_counts_between_the_baseline_sizes(ctx, bits, k):
+    """12 and 48 limbs (the BASELINE configs are 16 / 32 / 64): random odd moduli and random signatures below them - not
+    valid signatures, which does not matter for the arithmetic: sig^65537 mod n, the 19 carry chains and the PKCS#1
+    comparison must produce the oracle's table cell for cell, with is_valid = 0"""
+    import random
+    r = random.Random(bits)
+    nl = bits // 64
+    ns, ss, hs = [], [], []
+    for _ in range(2):
+        n = r.getrandbits(bits) | (1 << (bits - 1)) | 1
+        ns.append(CO.int_to_limbs64(n, nl)); ss.append(CO.int_to_limbs64(r.getrandbits(bits) % n, nl)); hs.append(CO.int_to_limbs64(r.getrandbits(256), 4))
+    prog = ctx.rsa_program(bits, k)
+    adv, valid = prog.witness_batch(np.stack(ns), np.stack(ss), np.stack(hs))
+    assert valid.tolist() == [0, 0]
+    for i in range(2):
+        t = CO.RsaTable(bits, k)
+        assert t.synthesize(ns[i], ss[i], hs[i]) == 0
+        assert prog.info()["rows_used"] == t.rows()
+        assert np.array_equal(adv[i], t.advice())
+        t.free()
+    prog.free()
+
+
 def test_layout_errors(ctx):
     import b2rsa
     with pytest.raises(b2rsa.B2RError) as e:
