@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "..", "lib", "libb2rsa.so")
+LIB_PATH = os.environ.get("B2R_LIB") or os.path.join(_HERE, "..", "lib", "libb2rsa.so")   # B2R_LIB: A/B builds during kernel work
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_LAYOUT, ERR_SYNTH = -1, -2, -3, -4, -5, -6

@@ -45,7 +45,7 @@ B2R_HD xyzz_t xyzz_double_affine(const affine_t& p) {
     fe_t M = Fq::add(Fq::dbl(xx), xx);
     xyzz_t r;
     r.x = Fq::sub(Fq::sqr(M), Fq::dbl(S));
-    r.y = Fq::sub(Fq::mul(M, Fq::sub(S, r.x)), Fq::mul(W, p.y));
+    r.y = Fq::mul_sub_mul(M, Fq::sub(S, r.x), W, p.y);
     r.zz = V;
     r.zzz = W;
     return r;  // y == 0 cannot happen on a prime-order curve
@@ -61,7 +61,7 @@ B2R_HD xyzz_t xyzz_double(const xyzz_t& p) {
     fe_t M = Fq::add(Fq::dbl(xx), xx);
     xyzz_t r;
     r.x = Fq::sub(Fq::sqr(M), Fq::dbl(S));
-    r.y = Fq::sub(Fq::mul(M, Fq::sub(S, r.x)), Fq::mul(W, p.y));
+    r.y = Fq::mul_sub_mul(M, Fq::sub(S, r.x), W, p.y);
     r.zz = Fq::mul(V, p.zz);
     r.zzz = Fq::mul(W, p.zzz);
     return r;
@@ -97,7 +97,7 @@ B2R_HD void xyzz_madd(xyzz_t& acc, const affine_t& q, bool neg) {
     fe_t PPP = Fq::mul(P, PP);
     fe_t Q = Fq::mul(acc.x, PP);
     fe_t X3 = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
-    fe_t Y3 = Fq::sub(Fq::mul(R, Fq::sub(Q, X3)), Fq::mul(acc.y, PPP));
+    fe_t Y3 = Fq::mul_sub_mul(R, Fq::sub(Q, X3), acc.y, PPP);   // one reduction for both products
     acc.x = X3;
     acc.y = Y3;
     acc.zz = Fq::mul(acc.zz, PP);
@@ -129,13 +129,16 @@ B2R_HD void xyzz_add(xyzz_t& acc, const xyzz_t& q) {
     fe_t PPP = Fq::mul(P, PP);
     fe_t Q = Fq::mul(U1, PP);
     fe_t X3 = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
-    fe_t Y3 = Fq::sub(Fq::mul(R, Fq::sub(Q, X3)), Fq::mul(S1, PPP));
+    fe_t Y3 = Fq::mul_sub_mul(R, Fq::sub(Q, X3), S1, PPP);
     acc.x = X3;
     acc.y = Y3;
     acc.zz = Fq::mul(Fq::mul(acc.zz, q.zz), PP);
     acc.zzz = Fq::mul(Fq::mul(acc.zzz, q.zzz), PPP);
 }
 
+#ifndef B2R_MADD_RR
+#define B2R_MADD_RR(R) Fq::mul(R, R)
+#endif
 // ---- lock-step variants -----------------------------------------------------------------------
 // Same results as xyzz_madd / xyzz_add, written so that all lanes of a warp execute the same
 // instruction stream: the general formulas run unconditionally and the identity cases are
@@ -155,13 +158,21 @@ B2R_HD xyzz_t xyzz_from_affine_signed(const affine_t& p, bool neg) {
     return r;
 }
 B2R_HD void xyzz_madd_ls(xyzz_t& acc, const affine_t& q, bool neg) {
-    const bool q_id = affine_is_identity(q), a_id = xyzz_is_identity(acc);
+    // identity operands leave through rare (possibly divergent) branches: real base tables hold no identity points and
+    // a running sum only becomes the identity through P - P.  The general case then updates acc in place, products
+    // ordered so that every operand dies at its last use (no selects holding the old sum alive next to the new one).
+    if (affine_is_identity(q)) return;
     fe_t qy = neg ? Fq::neg(q.y) : q.y;
-    fe_t U2 = Fq::mul(q.x, acc.zz);
-    fe_t S2 = Fq::mul(qy, acc.zzz);
-    fe_t P = Fq::sub(U2, acc.x);
-    fe_t R = Fq::sub(S2, acc.y);
-    if (!q_id && !a_id && Fq::is_zero(P)) {
+    if (xyzz_is_identity(acc)) {
+        acc.x = q.x;
+        acc.y = qy;
+        acc.zz = Fq::one();
+        acc.zzz = Fq::one();
+        return;
+    }
+    fe_t P = Fq::sub(Fq::mul(q.x, acc.zz), acc.x);
+    fe_t R = Fq::sub(Fq::mul(qy, acc.zzz), acc.y);
+    if (Fq::is_zero(P)) {
         if (Fq::is_zero(R)) {
             affine_t t;
             t.x = q.x;
@@ -173,26 +184,14 @@ B2R_HD void xyzz_madd_ls(xyzz_t& acc, const affine_t& q, bool neg) {
         return;
     }
     fe_t PP = Fq::sqr(P);
-    fe_t PPP = Fq::mul(P, PP);
+    acc.zz = Fq::mul(acc.zz, PP);
     fe_t Q = Fq::mul(acc.x, PP);
-    // R^2 through the general product: seven values are live here, and the dedicated squaring's extra accumulator
-    // words push k_accum_entries (127 registers at 4 CTAs/SM) into spills - measured slower than it saves
-    fe_t X3 = Fq::sub(Fq::sub(Fq::mul(R, R), PPP), Fq::dbl(Q));
-    fe_t Y3 = Fq::sub(Fq::mul(R, Fq::sub(Q, X3)), Fq::mul(acc.y, PPP));
-    fe_t ZZ3 = Fq::mul(acc.zz, PP);
-    fe_t ZZZ3 = Fq::mul(acc.zzz, PPP);
-    if (a_id) {
-        X3 = q.x;
-        Y3 = qy;
-        ZZ3 = Fq::one();
-        ZZZ3 = Fq::one();
-    }
-    if (!q_id) {
-        acc.x = X3;
-        acc.y = Y3;
-        acc.zz = ZZ3;
-        acc.zzz = ZZZ3;
-    }
+    fe_t PPP = Fq::mul(P, PP);
+    acc.zzz = Fq::mul(acc.zzz, PPP);
+    // R^2 through the general product (the dedicated squaring's extra accumulator words spill at 127 registers)
+    acc.x = Fq::sub(Fq::sub(B2R_MADD_RR(R), PPP), Fq::dbl(Q));
+    // Y3 = R (Q - X3) - Y1 PPP with one reduction for both products
+    acc.y = Fq::mul_sub_mul(R, Fq::sub(Q, acc.x), acc.y, PPP);
 }
 B2R_HD void xyzz_add_ls(xyzz_t& acc, const xyzz_t& q) {
     const bool q_id = xyzz_is_identity(q), a_id = xyzz_is_identity(acc);
@@ -211,7 +210,7 @@ B2R_HD void xyzz_add_ls(xyzz_t& acc, const xyzz_t& q) {
     fe_t PPP = Fq::mul(P, PP);
     fe_t Q = Fq::mul(U1, PP);
     fe_t X3 = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
-    fe_t Y3 = Fq::sub(Fq::mul(R, Fq::sub(Q, X3)), Fq::mul(S1, PPP));
+    fe_t Y3 = Fq::mul_sub_mul(R, Fq::sub(Q, X3), S1, PPP);
     fe_t ZZ3 = Fq::mul(Fq::mul(acc.zz, q.zz), PP);
     fe_t ZZZ3 = Fq::mul(Fq::mul(acc.zzz, q.zzz), PPP);
     if (a_id) {

@@ -402,6 +402,93 @@ struct Field {
         final_sub(r.l);
         return r;
     }
+    // a*b + c*d (Montgomery, fully reduced) with ONE reduction: the rows of both products go into the same pair of
+    // accumulators before the m * p rows of the iteration - 192 wide MADs instead of the 256 of two products.
+    // Inputs < p (c may equal p: see mul_sub_mul).  Bounds: at iteration start T < a + c + p <= 3p < 2^256 (p < 2^253.6),
+    // inside an iteration T + a b_i + c d_i + p m < (a + c + p) 2^32 < 2^288, so the S lanes (words 1..8) never carry out
+    // and the P lanes need their carry word; the result (a b + c d + M p) / 2^256 < p (2p / 2^256 + 1) < 1.38 p: one
+    // conditional subtraction.
+    B2R_HD static fe_t mul_add_mul(const fe_t& a, const fe_t& b, const fe_t& c, const fe_t& d) {
+        uint32_t m[8];
+        for (int i = 0; i < 8; i++) m[i] = P::MOD(i);
+        uint32_t Pw[10], Sw[10];
+        row_mul(Pw, &a.l[0], b.l[0]);
+        row_mul(Sw, &a.l[1], b.l[0]);
+        Pw[8] = row_mad(Pw, &c.l[0], d.l[0]);
+        row_mad_nc(Sw, &c.l[1], d.l[0]);
+        uint32_t mi = Pw[0] * P::N0INV;
+        Pw[8] += row_mad(Pw, &m[0], mi);
+        row_mad_nc(Sw, &m[1], mi);
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            row_shift_mad(Pw, &Sw[0], &a.l[1], b.l[i]);
+            uint32_t nP[10], nS[10];
+            for (int k = 0; k < 8; k++) nS[k] = Pw[k + 2];
+            for (int k = 0; k < 8; k++) nP[k] = Sw[k];
+            nP[8] = row_mad(nP, &a.l[0], b.l[i]);
+            nP[8] += row_mad(nP, &c.l[0], d.l[i]);
+            row_mad_nc(nS, &c.l[1], d.l[i]);
+            mi = nP[0] * P::N0INV;
+            nP[8] += row_mad(nP, &m[0], mi);
+            row_mad_nc(nS, &m[1], mi);
+            for (int k = 0; k < 9; k++) Pw[k] = nP[k];
+            for (int k = 0; k < 8; k++) Sw[k] = nS[k];
+        }
+        fe_t r;
+        add8(r.l, Sw, &Pw[1]);
+        final_sub(r.l);
+        return r;
+    }
+    // a*b - c*d = a*b + (p - c)*d; c = 0 gives the multiplicand p (adds p*d: still in the bounds above)
+    B2R_HD static fe_t mul_sub_mul(const fe_t& a, const fe_t& b, const fe_t& c, const fe_t& d) {
+        fe_t nc;
+        uint32_t m[8];
+        for (int i = 0; i < 8; i++) m[i] = P::MOD(i);
+        sub8(nc.l, m, c.l);
+        return mul_add_mul(a, b, nc, d);
+    }
+    // sum of four products with one reduction (320 wide MADs instead of 512).  T < a0 + a1 + a2 + a3 + p <= 5p < 2^256
+    // at iteration start, < 2^288 inside; result < p (4p / 2^256 + 1) < 1.76 p.
+    B2R_HD static fe_t dot4(const fe_t& a0, const fe_t& b0, const fe_t& a1, const fe_t& b1, const fe_t& a2, const fe_t& b2, const fe_t& a3,
+                            const fe_t& b3) {
+        uint32_t m[8];
+        for (int i = 0; i < 8; i++) m[i] = P::MOD(i);
+        uint32_t Pw[10], Sw[10];
+        row_mul(Pw, &a0.l[0], b0.l[0]);
+        row_mul(Sw, &a0.l[1], b0.l[0]);
+        Pw[8] = row_mad(Pw, &a1.l[0], b1.l[0]);
+        row_mad_nc(Sw, &a1.l[1], b1.l[0]);
+        Pw[8] += row_mad(Pw, &a2.l[0], b2.l[0]);
+        row_mad_nc(Sw, &a2.l[1], b2.l[0]);
+        Pw[8] += row_mad(Pw, &a3.l[0], b3.l[0]);
+        row_mad_nc(Sw, &a3.l[1], b3.l[0]);
+        uint32_t mi = Pw[0] * P::N0INV;
+        Pw[8] += row_mad(Pw, &m[0], mi);
+        row_mad_nc(Sw, &m[1], mi);
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            row_shift_mad(Pw, &Sw[0], &a0.l[1], b0.l[i]);
+            uint32_t nP[10], nS[10];
+            for (int k = 0; k < 8; k++) nS[k] = Pw[k + 2];
+            for (int k = 0; k < 8; k++) nP[k] = Sw[k];
+            nP[8] = row_mad(nP, &a0.l[0], b0.l[i]);
+            nP[8] += row_mad(nP, &a1.l[0], b1.l[i]);
+            row_mad_nc(nS, &a1.l[1], b1.l[i]);
+            nP[8] += row_mad(nP, &a2.l[0], b2.l[i]);
+            row_mad_nc(nS, &a2.l[1], b2.l[i]);
+            nP[8] += row_mad(nP, &a3.l[0], b3.l[i]);
+            row_mad_nc(nS, &a3.l[1], b3.l[i]);
+            mi = nP[0] * P::N0INV;
+            nP[8] += row_mad(nP, &m[0], mi);
+            row_mad_nc(nS, &m[1], mi);
+            for (int k = 0; k < 9; k++) Pw[k] = nP[k];
+            for (int k = 0; k < 8; k++) Sw[k] = nS[k];
+        }
+        fe_t r;
+        add8(r.l, Sw, &Pw[1]);
+        final_sub(r.l);
+        return r;
+    }
     // Montgomery square.  The 28 cross products a_i a_j (i < j) are gathered first - row i feeds an even-aligned and
     // an odd-aligned 64-bit-lane accumulator, rows in order so that every carry out lands on a word that holds only
     // earlier carries - then doubled (funnel shifts), the 8 squares added on top (one carry chain), and the 16-word

@@ -40,6 +40,11 @@ static void run(const char* name, int n) {
         pr(a); pr(b); pr(F::mul(a, b)); pr(F::add(a, b)); pr(F::sub(a, b)); pr(F::neg(a));
         if (it < 8) pr(F::inv(a)); else pr(it < 200 ? F::inv_vartime(a) : F::zero());
         pr(F::sqr(a));
+        // fused sums of products (one reduction): extremes p - 1..p - 4 in every operand every 13th vector
+        fe_t c = rand_fe<P>(it % 13 == 12 ? 2 : (it % 17 == 16 ? 3 : 0)), d = rand_fe<P>(it % 13 == 12 ? 2 : 0);
+        if (it % 13 == 12) { a = rand_fe<P>(2); b = rand_fe<P>(2); }
+        pr(a); pr(b); pr(c); pr(d);
+        pr(F::mul_add_mul(a, b, c, d)); pr(F::mul_sub_mul(a, b, c, d)); pr(F::dot4(a, b, c, d, a, c, b, d));
         printf("\n");
     }
 }

@@ -29,5 +29,9 @@ def test_field_cuh_host_build_matches_python():
         if inv:
             # Montgomery inverse: inv(aR) = a^-1 R  =>  a_m * inv_m = R^2 (mod p)
             assert a * inv % mod == R * R % mod
+        a, b, c, d, mam, msm, dot4 = (int(x, 16) for x in f[9:16])
+        assert mam == (a * b + c * d) * rinv % mod       # one reduction for two products
+        assert msm == (a * b - c * d) * rinv % mod
+        assert dot4 == (a * b + c * d + a * c + b * d) * rinv % mod
         n += 1
     assert n == 1200
