@@ -297,8 +297,8 @@ k_lookup_numden(const fe_t* __restrict__ P, const fe_t* __restrict__ fixed_value
     if (row >= n) return;
     const fe_t theta = ldv(chal + (size_t)p * 8), beta = ldv(chal + (size_t)p * 8 + 1), gamma = ldv(chal + (size_t)p * 8 + 2);
     const fe_t adv = ldv(P + ((size_t)(SL_ADV + lookup_acol(li)) * B + p) * n + row);
-    const fe_t A = Fr::add(Fr::mul(ldv_nc(fixed_values + (size_t)lookup_ftag(li) * n + row), theta),
-                           Fr::mul(ldv_nc(fixed_values + (size_t)lookup_fsel(li) * n + row), adv));
+    const fe_t A = Fr::mul_add_mul(ldv_nc(fixed_values + (size_t)lookup_ftag(li) * n + row), theta,
+                                   ldv_nc(fixed_values + (size_t)lookup_fsel(li) * n + row), adv);
     const fe_t S = Fr::add(Fr::mul(ldv_nc(fixed_values + (size_t)FX_T_TAG * n + row), theta), ldv_nc(fixed_values + (size_t)FX_T_VALUE * n + row));
     const fe_t ap = ldv(P + ((size_t)(SL_LA + 2 * li) * B + p) * n + row), sp = ldv(P + ((size_t)(SL_LA + 2 * li + 1) * B + p) * n + row);
     const size_t o = ((size_t)(NSETS + li) * B + p) * n + row;
@@ -447,44 +447,47 @@ __global__ void __launch_bounds__(128, B2R_QMINB) k_quotient(const QuotArgs A, c
     auto wy = [&](const fe_t& e, int k) { return Fr::mul(e, ldv_nc(yp + k)); };
     // the advice values are re-read where they are used (L1 hits) instead of being held in 40 registers across the kernel
     auto adv = [&](int c) { return c < NADV ? ext(SL_ADV + c, i) : Fr::zero(); };
+    // Sums of products share ONE Montgomery reduction (Fr::dot4 / mul_add_mul / mul_sub_mul: 64 wide MADs per product
+    // plus 64 per sum instead of 128 per product) - 28 of the kernel's 110 reductions go, values unchanged.
+    auto yw = [&](int k) { return ldv_nc(yp + k); };
     // main gate
     fe_t gate;
     {
-        const fe_t a = adv(0), b = adv(1);
-        gate = Fr::mul(a, fx(FX_SA));
-        gate = Fr::add(gate, Fr::mul(b, fx(FX_SB)));
-        gate = Fr::add(gate, Fr::mul(Fr::mul(a, b), fx(FX_MUL_AB)));
+        const fe_t a = adv(0), b = adv(1), c = adv(2);
+        gate = Fr::dot4(a, fx(FX_SA), b, fx(FX_SB), Fr::mul(a, b), fx(FX_MUL_AB), c, fx(FX_SC));
+        const fe_t d = adv(3);
+        gate = Fr::add(gate, Fr::dot4(d, fx(FX_SD), Fr::mul(c, d), fx(FX_MUL_CD), adv(4), fx(FX_SE), ext(SL_ADV + 4, nx), fx(FX_SE_NEXT)));
     }
-    {
-        const fe_t c = adv(2), d = adv(3);
-        gate = Fr::add(gate, Fr::mul(c, fx(FX_SC)));
-        gate = Fr::add(gate, Fr::mul(d, fx(FX_SD)));
-        gate = Fr::add(gate, Fr::mul(Fr::mul(c, d), fx(FX_MUL_CD)));
-    }
-    gate = Fr::add(gate, Fr::mul(adv(4), fx(FX_SE)));
-    gate = Fr::add(gate, Fr::mul(ext(SL_ADV + 4, nx), fx(FX_SE_NEXT)));
     gate = Fr::add(gate, fx(FX_CONST));
-    fe_t acc = wy(gate, 0);
     const fe_t one = Fr::one();
     // permutation argument
     fe_t pz[NSETS];
     for (int s = 0; s < NSETS; s++) pz[s] = ext(SL_PZ + s, i);
-    fe_t g0 = wy(Fr::sub(one, pz[0]), 1);                                                   // l0 group
-    fe_t glast = wy(Fr::sub(Fr::sqr(pz[NSETS - 1]), pz[NSETS - 1]), 2);                     // l_last group
-    g0 = Fr::add(g0, wy(Fr::sub(pz[1], ext(SL_PZ, lastr)), 3));
+    fe_t g0 = Fr::mul_add_mul(Fr::sub(one, pz[0]), yw(1), Fr::sub(pz[1], ext(SL_PZ, lastr)), yw(3));   // l0 group
+    fe_t glast = wy(Fr::sub(Fr::sqr(pz[NSETS - 1]), pz[NSETS - 1]), 2);                               // l_last group
     // X at this point of the coset: zeta * omega_ext^i
     const uint32_t half = A.ext_n >> 1;
     fe_t xi = i < half ? ldv_nc(A.tw_ext + i) : Fr::neg(ldv_nc(A.tw_ext + (i - half)));
     const fe_t beta_x = Fr::mul(beta, Fr::mul(xi, C.zeta));
-    fe_t gact = Fr::zero();                                                                 // l_active group
-    for (int s = 0; s < NSETS; s++) {
-        fe_t left = ext(SL_PZ + s, nx), right = pz[s];
-        for (int c = s * CHUNK; c < (s + 1) * CHUNK && c < NPERM; c++) {
-            const fe_t vg = Fr::add(adv(c), gamma);
-            left = Fr::mul(left, Fr::add(Fr::mul(beta, ldv_nc(A.sigma_c + (size_t)c * A.ext_n + i)), vg));
-            right = Fr::mul(right, Fr::add(Fr::mul(beta_x, C.delta_pows[c]), vg));
+    fe_t gact;                                                                              // l_active group
+    {
+        fe_t pd[NSETS];
+        for (int s = 0; s < NSETS; s++) {
+            fe_t left = ext(SL_PZ + s, nx), right = pz[s];
+            const int c_end = (s + 1) * CHUNK < NPERM ? (s + 1) * CHUNK : NPERM;
+            for (int c = s * CHUNK; c < c_end; c++) {
+                const fe_t vg = Fr::add(adv(c), gamma);
+                const fe_t fl = Fr::add(Fr::mul(beta, ldv_nc(A.sigma_c + (size_t)c * A.ext_n + i)), vg);
+                const fe_t fr = Fr::add(Fr::mul(beta_x, C.delta_pows[c]), vg);
+                if (c + 1 < c_end) {
+                    left = Fr::mul(left, fl);
+                    right = Fr::mul(right, fr);
+                } else {
+                    pd[s] = Fr::mul_sub_mul(left, fl, right, fr);   // left - right of the set
+                }
+            }
         }
-        gact = Fr::add(gact, wy(Fr::sub(left, right), 4 + s));
+        gact = Fr::mul_add_mul(pd[0], yw(4), pd[1], yw(5));
     }
     // lookup arguments
     const fe_t tbl_g = Fr::add(Fr::add(Fr::mul(fx(FX_T_TAG), theta), fx(FX_T_VALUE)), gamma);
@@ -493,21 +496,15 @@ __global__ void __launch_bounds__(128, B2R_QMINB) k_quotient(const QuotArgs A, c
 #pragma unroll 1
     for (int l = 0; l < NLOOK; l++) {
         const int k0 = 4 + NSETS + 5 * l;
-        const fe_t z = ext(SL_LZ + l, i), zn = ext(SL_LZ + l, nx), ap = ext(SL_LA + 2 * l, i), sp = ext(SL_LA + 2 * l + 1, i),
-                   apv = ext(SL_LA + 2 * l, pv);
-        const fe_t inp = l < 4 ? Fr::add(tag_c, Fr::mul(s_c, adv(l))) : Fr::add(tag_o, Fr::mul(s_o, adv(0)));
-        g0 = Fr::add(g0, wy(Fr::sub(one, z), k0));
-        glast = Fr::add(glast, wy(Fr::sub(Fr::sqr(z), z), k0 + 1));
-        const fe_t left = Fr::mul(Fr::mul(zn, Fr::add(ap, beta)), Fr::add(sp, gamma));
-        const fe_t right = Fr::mul(Fr::mul(z, Fr::add(inp, beta)), tbl_g);
-        gact = Fr::add(gact, wy(Fr::sub(left, right), k0 + 2));
+        const fe_t z = ext(SL_LZ + l, i), ap = ext(SL_LA + 2 * l, i), sp = ext(SL_LA + 2 * l + 1, i);
         const fe_t d = Fr::sub(ap, sp);
-        g0 = Fr::add(g0, wy(d, k0 + 3));
-        gact = Fr::add(gact, wy(Fr::mul(d, Fr::sub(ap, apv)), k0 + 4));
+        g0 = Fr::add(g0, Fr::mul_add_mul(Fr::sub(one, z), yw(k0), d, yw(k0 + 3)));
+        glast = Fr::add(glast, wy(Fr::sub(Fr::sqr(z), z), k0 + 1));
+        const fe_t inp = l < 4 ? Fr::add(tag_c, Fr::mul(s_c, adv(l))) : Fr::add(tag_o, Fr::mul(s_o, adv(0)));
+        const fe_t lr = Fr::mul_sub_mul(Fr::mul(ext(SL_LZ + l, nx), Fr::add(ap, beta)), Fr::add(sp, gamma), Fr::mul(z, Fr::add(inp, beta)), tbl_g);
+        gact = Fr::add(gact, Fr::mul_add_mul(lr, yw(k0 + 2), Fr::mul(d, Fr::sub(ap, ext(SL_LA + 2 * l, pv))), yw(k0 + 4)));
     }
-    acc = Fr::add(acc, Fr::mul(ldv_nc(A.l_c + i), g0));
-    acc = Fr::add(acc, Fr::mul(ldv_nc(A.l_c + (size_t)A.ext_n + i), glast));
-    acc = Fr::add(acc, Fr::mul(ldv_nc(A.l_c + 2 * (size_t)A.ext_n + i), gact));
+    const fe_t acc = Fr::dot4(gate, yw(0), ldv_nc(A.l_c + i), g0, ldv_nc(A.l_c + (size_t)A.ext_n + i), glast, ldv_nc(A.l_c + 2 * (size_t)A.ext_n + i), gact);
     stv(A.h + (size_t)q * A.ext_n + i, Fr::mul(acc, C.t_inv[i & (A.step - 1)]));
 }
 
@@ -573,8 +570,12 @@ k_lincomb(const PolyTable T, const LincombPlan* __restrict__ plan, const fe_t* _
     if (row >= T.n) return;
     const uint32_t m = plan->nterms[g];
     const fe_t* sc = scal + ((size_t)p * NPOINTS + g) * MAXTERMS;
+    auto term = [&](uint32_t j) { return ldv(poly_ptr(T, plan->poly[g][j], p) + row); };
     fe_t acc = Fr::zero();
-    for (uint32_t j = 0; j < m; j++) acc = Fr::add(acc, Fr::mul(ldv_nc(sc + j), ldv(poly_ptr(T, plan->poly[g][j], p) + row)));
+    uint32_t j = 0;
+    for (; j + 4 <= m; j += 4)   // four terms per Montgomery reduction
+        acc = Fr::add(acc, Fr::dot4(ldv_nc(sc + j), term(j), ldv_nc(sc + j + 1), term(j + 1), ldv_nc(sc + j + 2), term(j + 2), ldv_nc(sc + j + 3), term(j + 3)));
+    for (; j < m; j++) acc = Fr::add(acc, Fr::mul(ldv_nc(sc + j), term(j)));
     stv(out + ((size_t)p * NPOINTS + g) * T.n + row, acc);
 }
 // q = (f(X) - f(z)) / (X - z): q_{i-1} = c_i + z q_i.  One CTA per polynomial; thread = n/256 consecutive coefficients:
