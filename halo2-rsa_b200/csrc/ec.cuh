@@ -136,9 +136,6 @@ B2R_HD void xyzz_add(xyzz_t& acc, const xyzz_t& q) {
     acc.zzz = Fq::mul(Fq::mul(acc.zzz, q.zzz), PPP);
 }
 
-#ifndef B2R_MADD_RR
-#define B2R_MADD_RR(R) Fq::mul(R, R)
-#endif
 // ---- lock-step variants -----------------------------------------------------------------------
 // Same results as xyzz_madd / xyzz_add, written so that all lanes of a warp execute the same
 // instruction stream: the general formulas run unconditionally and the identity cases are
@@ -188,8 +185,7 @@ B2R_HD void xyzz_madd_ls(xyzz_t& acc, const affine_t& q, bool neg) {
     fe_t Q = Fq::mul(acc.x, PP);
     fe_t PPP = Fq::mul(P, PP);
     acc.zzz = Fq::mul(acc.zzz, PPP);
-    // R^2 through the general product (the dedicated squaring's extra accumulator words spill at 127 registers)
-    acc.x = Fq::sub(Fq::sub(B2R_MADD_RR(R), PPP), Fq::dbl(Q));
+    acc.x = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
     // Y3 = R (Q - X3) - Y1 PPP with one reduction for both products
     acc.y = Fq::mul_sub_mul(R, Fq::sub(Q, acc.x), acc.y, PPP);
 }

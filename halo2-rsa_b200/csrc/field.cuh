@@ -209,56 +209,6 @@ B2R_HD void lanes_mad_c(uint32_t* X, const uint32_t* a, uint32_t w) {
 #endif
 }
 
-// r[0..n-1] = a + b + cin over n words (n = 7 or 8), returns the carry out
-template <int N>
-B2R_HD uint32_t addn_cin(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t cin) {
-    uint32_t c;
-#if defined(__CUDA_ARCH__)
-    static_assert(N == 7, "addn_cin: 7 words");
-    asm("add.cc.u32 %7, %22, 0xffffffff;"
-        "addc.cc.u32 %0, %8, %15; addc.cc.u32 %1, %9, %16; addc.cc.u32 %2, %10, %17; addc.cc.u32 %3, %11, %18;"
-        "addc.cc.u32 %4, %12, %19; addc.cc.u32 %5, %13, %20; addc.cc.u32 %6, %14, %21; addc.u32 %7, 0, 0;"
-        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(c)
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]),
-          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(cin));
-#else
-    uint64_t cy = cin;
-    for (int i = 0; i < N; i++) {
-        uint64_t t = (uint64_t)a[i] + b[i] + cy;
-        r[i] = (uint32_t)t;
-        cy = t >> 32;
-    }
-    c = (uint32_t)cy;
-#endif
-    return c;
-}
-
-// T[0..7] = D[0..7] + the squares a[0]^2, a[1]^2, a[2]^2, a[3]^2 laid out on lanes (2l, 2l+1), carry in / out
-B2R_HD uint32_t sqr_diag4(uint32_t* T, const uint32_t* D, const uint32_t* a, uint32_t cin) {
-    uint32_t c;
-#if defined(__CUDA_ARCH__)
-    asm("add.cc.u32 %8, %21, 0xffffffff;"
-        "madc.lo.cc.u32 %0, %17, %17, %9; madc.hi.cc.u32 %1, %17, %17, %10;"
-        "madc.lo.cc.u32 %2, %18, %18, %11; madc.hi.cc.u32 %3, %18, %18, %12;"
-        "madc.lo.cc.u32 %4, %19, %19, %13; madc.hi.cc.u32 %5, %19, %19, %14;"
-        "madc.lo.cc.u32 %6, %20, %20, %15; madc.hi.cc.u32 %7, %20, %20, %16; addc.u32 %8, 0, 0;"
-        : "=&r"(T[0]), "=&r"(T[1]), "=&r"(T[2]), "=&r"(T[3]), "=&r"(T[4]), "=&r"(T[5]), "=&r"(T[6]), "=&r"(T[7]), "=&r"(c)
-        : "r"(D[0]), "r"(D[1]), "r"(D[2]), "r"(D[3]), "r"(D[4]), "r"(D[5]), "r"(D[6]), "r"(D[7]),
-          "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(cin));
-#else
-    uint64_t cy = cin;
-    for (int l = 0; l < 4; l++) {
-        uint64_t x = (uint64_t)D[2 * l] | ((uint64_t)D[2 * l + 1] << 32);
-        unsigned __int128 t = (unsigned __int128)a[l] * a[l] + x + cy;
-        T[2 * l] = (uint32_t)t;
-        T[2 * l + 1] = (uint32_t)(t >> 32);
-        cy = (uint64_t)(t >> 64);
-    }
-    c = (uint32_t)cy;
-#endif
-    return c;
-}
-
 // 8-word add / sub with carry chains
 B2R_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     uint32_t c;
@@ -489,63 +439,61 @@ struct Field {
         final_sub(r.l);
         return r;
     }
-    // Montgomery square.  The 28 cross products a_i a_j (i < j) are gathered first - row i feeds an even-aligned and
-    // an odd-aligned 64-bit-lane accumulator, rows in order so that every carry out lands on a word that holds only
-    // earlier carries - then doubled (funnel shifts), the 8 squares added on top (one carry chain), and the 16-word
-    // result reduced by the same two-accumulator loop as mul() without its a*b rows: 36 + 64 wide MADs instead of 128.
+    // iteration I >= 1 of sqr(): shift fused with the odd lanes of m * p, even lanes of m * p, then row I of the square
+    template <int I>
+    B2R_HD static void sqr_step(uint32_t* Pw, uint32_t* Sw, const uint32_t* a, const uint32_t* D, const uint32_t* m) {
+        const uint32_t mi = (Sw[0] + Pw[1]) * P::N0INV;
+        row_shift_mad(Pw, &Sw[0], &m[1], mi);
+        uint32_t nP[10], nS[10];
+        for (int k = 0; k < 8; k++) nS[k] = Pw[k + 2];
+        for (int k = 0; k < 8; k++) nP[k] = Sw[k];
+        nS[8] = 0;
+        nP[8] = row_mad(nP, &m[0], mi);
+        uint32_t V[9];
+        for (int k = 0; k < 8; k++) V[k] = D[k];
+        V[8] = 0;
+        V[I] = a[I];
+        if constexpr (I < 7) V[I + 1] = D[I + 1] & ~1u;
+        constexpr int le = (I + 1) / 2, lo = I / 2;   // first even-position lane (P) / odd-position lane (S) of the row
+        if constexpr (le < 4) lanes_mad_c<4 - le>(&nP[2 * le], &V[2 * le], a[I]);
+        lanes_mad_c<4 - lo>(&nS[2 * lo], &V[2 * lo + 1], a[I]);   // carry word nS[8] stays 0: the S lanes never carry out (bound)
+        for (int k = 0; k < 9; k++) Pw[k] = nP[k];
+        for (int k = 0; k < 8; k++) Sw[k] = nS[k];
+    }
+    // Montgomery square, interleaved like mul(): iteration i adds a_i * (a_i, 2a_{i+1}, .., 2a_7) at relative word
+    // positions i..7 - the doubled cross terms come from the words of D = 2a (a < 2^254), with the bit that a_i shifted
+    // into D_{i+1} cleared - and then the m * p row: 36 + 64 wide MADs instead of 128, in the register footprint of
+    // mul().  (The first version gathered all 16 words of a^2 before reducing: two 16-word accumulators, which spilled
+    // wherever a point addition wanted R^2 next to six other live values.)  Row i >= 1 does not touch relative word 0,
+    // so m is known before the row is added and the shift is fused with the odd lanes of m * p.
+    // Bounds as in mul(): the window stays below (2a + p) 2^32 < 2^288, the result below 1.19 p.
     B2R_HD static fe_t sqr(const fe_t& a) {
-        uint32_t E[16], O[16];
-        for (int i = 0; i < 16; i++) E[i] = O[i] = 0;
-        lanes_mad_c<3>(&E[2], &a.l[2], a.l[0]);
-        lanes_mad_c<4>(&O[1], &a.l[1], a.l[0]);
-        lanes_mad_c<3>(&E[4], &a.l[3], a.l[1]);
-        lanes_mad_c<3>(&O[3], &a.l[2], a.l[1]);
-        lanes_mad_c<2>(&E[6], &a.l[4], a.l[2]);
-        lanes_mad_c<3>(&O[5], &a.l[3], a.l[2]);
-        lanes_mad_c<2>(&E[8], &a.l[5], a.l[3]);
-        lanes_mad_c<2>(&O[7], &a.l[4], a.l[3]);
-        lanes_mad_c<1>(&E[10], &a.l[6], a.l[4]);
-        lanes_mad_c<2>(&O[9], &a.l[5], a.l[4]);
-        lanes_mad_c<1>(&E[12], &a.l[7], a.l[5]);
-        lanes_mad_c<1>(&O[11], &a.l[6], a.l[5]);
-        lanes_mad_c<1>(&O[13], &a.l[7], a.l[6]);
-        // cross sum: words 1 .. 15 (word 0 is empty, word 1 is O alone)
-        uint32_t X[16];
-        X[0] = 0;
-        X[1] = O[1];
-        uint32_t c = addn_cin<7>(&X[2], &E[2], &O[2], 0);
-        c = addn_cin<7>(&X[9], &E[9], &O[9], c);   // words 9 .. 15; the sum fits 16 words
-        // doubled
-        uint32_t D[16];
-        D[0] = 0;
-        for (int k = 1; k < 16; k++) D[k] = (X[k] << 1) | (X[k - 1] >> 31);
-        // + squares
-        uint32_t T[16];
-        c = sqr_diag4(&T[0], &D[0], &a.l[0], 0);
-        (void)sqr_diag4(&T[8], &D[8], &a.l[4], c);
-        // Montgomery reduction of the low half, high half added at the end
         uint32_t m[8];
         for (int i = 0; i < 8; i++) m[i] = P::MOD(i);
+        uint32_t D[8];
+        D[0] = a.l[0] << 1;
+        for (int k = 1; k < 8; k++) D[k] = (a.l[k] << 1) | (a.l[k - 1] >> 31);
         uint32_t Pw[10], Sw[10];
-        for (int k = 0; k < 8; k++) Pw[k] = T[k];
+        {
+            uint32_t V[8];
+            V[0] = a.l[0];
+            V[1] = D[1] & ~1u;
+            for (int k = 2; k < 8; k++) V[k] = D[k];
+            row_mul(Pw, &V[0], a.l[0]);
+            row_mul(Sw, &V[1], a.l[0]);
+        }
         uint32_t mi = Pw[0] * P::N0INV;
         Pw[8] = row_mad(Pw, &m[0], mi);
-        row_mul(Sw, &m[1], mi);
-#pragma unroll
-        for (int i = 1; i < 8; i++) {
-            mi = (Sw[0] + Pw[1]) * P::N0INV;
-            row_shift_mad(Pw, &Sw[0], &m[1], mi);
-            uint32_t nP[10], nS[10];
-            for (int k = 0; k < 8; k++) nS[k] = Pw[k + 2];
-            for (int k = 0; k < 8; k++) nP[k] = Sw[k];
-            nP[8] = row_mad(nP, &m[0], mi);
-            for (int k = 0; k < 9; k++) Pw[k] = nP[k];
-            for (int k = 0; k < 8; k++) Sw[k] = nS[k];
-        }
+        row_mad_nc(Sw, &m[1], mi);
+        sqr_step<1>(Pw, Sw, a.l, D, m);
+        sqr_step<2>(Pw, Sw, a.l, D, m);
+        sqr_step<3>(Pw, Sw, a.l, D, m);
+        sqr_step<4>(Pw, Sw, a.l, D, m);
+        sqr_step<5>(Pw, Sw, a.l, D, m);
+        sqr_step<6>(Pw, Sw, a.l, D, m);
+        sqr_step<7>(Pw, Sw, a.l, D, m);
         fe_t r;
-        uint32_t u[8];
-        add8(u, Sw, &Pw[1]);     // <= p
-        add8(r.l, u, &T[8]);     // < 2p < 2^255
+        add8(r.l, Sw, &Pw[1]);
         final_sub(r.l);
         return r;
     }

@@ -945,18 +945,23 @@ __device__ __forceinline__ xyzz_t warp_weighted_sum(xyzz_t v, uint32_t lane, xyz
     if (lane == 0) v = xyzz_identity();
     return warp_tree_sum(v, lane);
 }
+// two warps per output u, side by side: the weighted sum of S1 (10 dependent additions) and the plain sum of A1 (5)
 __global__ void __launch_bounds__(128)
 k_br_level2_warp(const xyzz_t* __restrict__ S1, const xyzz_t* __restrict__ A1, uint32_t total_u, xyzz_t* __restrict__ L2) {
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= total_u) return;
-    xyzz_t tot;
-    const xyzz_t a2 = warp_weighted_sum(ld_xyzz(S1 + (size_t)w * 32 + lane), lane, tot);
-    const xyzz_t p1 = warp_tree_sum(ld_xyzz(A1 + (size_t)w * 32 + lane), lane);
-    if (lane == 0) {
-        xyzz_t* o = L2 + (size_t)w * 3;
-        st_xyzz(o, tot);
-        st_xyzz(o + 1, a2);
-        st_xyzz(o + 2, p1);
+    const uint32_t u = w >> 1;
+    if (u >= total_u) return;
+    xyzz_t* o = L2 + (size_t)u * 3;
+    if (w & 1u) {
+        const xyzz_t p1 = warp_tree_sum(ld_xyzz(A1 + (size_t)u * 32 + lane), lane);
+        if (lane == 0) st_xyzz(o + 2, p1);
+    } else {
+        xyzz_t tot;
+        const xyzz_t a2 = warp_weighted_sum(ld_xyzz(S1 + (size_t)u * 32 + lane), lane, tot);
+        if (lane == 0) {
+            st_xyzz(o, tot);
+            st_xyzz(o + 1, a2);
+        }
     }
 }
 __global__ void __launch_bounds__(96)
@@ -1167,7 +1172,7 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
     }
     B2R_LAUNCH_CHECK(ctx);
     const uint32_t total = (uint32_t)(G * nu);
-    if (warp_reduce) k_br_level2_warp<<<(unsigned)((G * 32 + 3) / 4), 128, 0, st>>>(s1, a1, (uint32_t)(G * 32), l2);
+    if (warp_reduce) k_br_level2_warp<<<(unsigned)((G * 64 + 3) / 4), 128, 0, st>>>(s1, a1, (uint32_t)(G * 32), l2);
     else k_br_level2<<<(total + 127) / 128, 128, 0, st>>>(s1, a1, nseg, nu, total, l2); }
     B2R_LAUNCH_CHECK(ctx);
     { KTimer kt(ctx, "msm_final");
