@@ -386,16 +386,16 @@ def main():
                     "avg_launch_ms": kms / kcnt, "share_of_step": kms / ms,
                     "note": "integer-multiplier bound (254-bit field products), not HBM bound: see int_pipe and DESIGN.md section 4"}
             # the roofline that binds this kernel (profiles/r01_pipebench.md): IMAD.WIDE issues at 32 lanes/clk/SM on B200, a
-            # Montgomery product is 128 of them, the dedicated squaring 100, a mixed addition 9 products + 1 squaring
-            # -> 148 SMs * 32 / 1252 additions per clock
+            # Montgomery product is 128 of them, the squaring 100, the fused a*b - c*d 192; a mixed addition is 6 products +
+            # 2 squarings + 1 fused pair (csrc/ec.cuh xyzz_madd_ls) = 1160 -> 148 SMs * 32 / 1160 additions per clock
             sm_clk = 1.965e9
-            ceiling = 148 * 32 / 1252.0 * sm_clk / 1e9
+            ceiling = 148 * 32 / 1160.0 * sm_clk / 1e9
             roof["int_pipe"] = {"unit": "G mixed additions/s", "achieved": accum_entries / (kms / 1e3) / 1e9, "peak": ceiling,
                                 "frac": accum_entries / (kms / 1e3) / 1e9 / ceiling,
                                 "additions_per_step": accum_entries / args.steps,
                                 "how": "bucket entries counted by the library (zero digits and, for the grand-product columns, rows where the "
                                        "column does not change are skipped) / kernel time; peak = 148 SMs x 32 IMAD.WIDE lanes/clk / "
-                                       "(9 products x 128 + 1 squaring x 100 IMAD.WIDE) at 1965 MHz"}
+                                       "(6 products x 128 + 2 squarings x 100 + 1 fused product pair x 192 = 1160 IMAD.WIDE per mixed addition) at 1965 MHz"}
             roof["traffic"], extra_t = recorded_traffic("k_accum_entries", MSM_SOURCES)
             roof.update(extra_t)
             if "ntt_pass" in prof:

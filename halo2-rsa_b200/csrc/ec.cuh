@@ -190,37 +190,31 @@ B2R_HD void xyzz_madd_ls(xyzz_t& acc, const affine_t& q, bool neg) {
     acc.y = Fq::mul_sub_mul(R, Fq::sub(Q, acc.x), acc.y, PPP);
 }
 B2R_HD void xyzz_add_ls(xyzz_t& acc, const xyzz_t& q) {
-    const bool q_id = xyzz_is_identity(q), a_id = xyzz_is_identity(acc);
+    // same shape as xyzz_madd_ls: identity operands and equal x leave through branches (whole warps of empty buckets are
+    // skipped by the callers' votes before they get here), the general case runs in place
+    if (xyzz_is_identity(q)) return;
+    if (xyzz_is_identity(acc)) {
+        acc = q;
+        return;
+    }
     fe_t U1 = Fq::mul(acc.x, q.zz);
-    fe_t U2 = Fq::mul(q.x, acc.zz);
     fe_t S1 = Fq::mul(acc.y, q.zzz);
-    fe_t S2 = Fq::mul(q.y, acc.zzz);
-    fe_t P = Fq::sub(U2, U1);
-    fe_t R = Fq::sub(S2, S1);
-    if (!q_id && !a_id && Fq::is_zero(P)) {
+    fe_t P = Fq::sub(Fq::mul(q.x, acc.zz), U1);
+    fe_t R = Fq::sub(Fq::mul(q.y, acc.zzz), S1);
+    if (Fq::is_zero(P)) {
         if (Fq::is_zero(R)) acc = xyzz_double(acc);
         else acc = xyzz_identity();
         return;
     }
+    acc.zz = Fq::mul(acc.zz, q.zz);
+    acc.zzz = Fq::mul(acc.zzz, q.zzz);
     fe_t PP = Fq::sqr(P);
-    fe_t PPP = Fq::mul(P, PP);
+    acc.zz = Fq::mul(acc.zz, PP);
     fe_t Q = Fq::mul(U1, PP);
-    fe_t X3 = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
-    fe_t Y3 = Fq::mul_sub_mul(R, Fq::sub(Q, X3), S1, PPP);
-    fe_t ZZ3 = Fq::mul(Fq::mul(acc.zz, q.zz), PP);
-    fe_t ZZZ3 = Fq::mul(Fq::mul(acc.zzz, q.zzz), PPP);
-    if (a_id) {
-        X3 = q.x;
-        Y3 = q.y;
-        ZZ3 = q.zz;
-        ZZZ3 = q.zzz;
-    }
-    if (!q_id) {
-        acc.x = X3;
-        acc.y = Y3;
-        acc.zz = ZZ3;
-        acc.zzz = ZZZ3;
-    }
+    fe_t PPP = Fq::mul(P, PP);
+    acc.zzz = Fq::mul(acc.zzz, PPP);
+    acc.x = Fq::sub(Fq::sub(Fq::sqr(R), PPP), Fq::dbl(Q));
+    acc.y = Fq::mul_sub_mul(R, Fq::sub(Q, acc.x), S1, PPP);
 }
 
 // normalise; identity -> (0, 0)

@@ -57,7 +57,10 @@ enum { SL_ADV = 0, SL_LA = 5 /* A'_l = 5+2l, S'_l = 6+2l */, SL_PZ = 15, SL_LZ =
 static constexpr int NZ = NSETS + NLOOK;  // grand products per proof
 static constexpr int NEVAL = 58, NPOINTS = 4, MAXTERMS = 52;
 static constexpr uint32_t MAX_TABLE = 1024;
-static constexpr int CH = 128;  // rows per thread in the grand-product kernels (one Fermat inversion per CH rows)
+#ifndef B2R_GP_CH
+#define B2R_GP_CH 256
+#endif
+static constexpr int CH = B2R_GP_CH;  // rows per thread in the grand-product kernels (one Fermat inversion per CH rows: 1.5 products per row at 256)
 
 __host__ __device__ inline int lookup_acol(int l) { return l < 4 ? l : 0; }
 __host__ __device__ inline int lookup_ftag(int l) { return l < 4 ? FX_TAG_COMP : FX_TAG_OVER; }
