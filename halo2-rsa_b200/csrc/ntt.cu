@@ -120,16 +120,20 @@ struct SwizzledTile {
 // thread takes rows r0, r0+q, r0+2q, r0+3q (q = a quarter of the current block), does the two butterflies of stage i and
 // the two of stage i+1 in registers (4 twiddle products, as two radix-2 stages would) and writes the 4 rows back:
 // half the shared-memory traffic and barriers of the plain radix-2 loop.  Ends with a barrier.
-template <int S, class Tile>
-__device__ __forceinline__ void ntt_tile_stages(const NttPassArgs& A, const Tile& tile, uint32_t c0) {
+// TWS: the pass's twiddles were staged in shared memory by ntt_stage_twiddles (passes behind the first one, where every
+// column of the CTA shares its twiddles): `tws` holds, round after round, w^ea / w^eb for rp < 2q and then w^ec for rp < q.
+template <int S, class Tile, bool TWS = false>
+__device__ __forceinline__ void ntt_tile_stages(const NttPassArgs& A, const Tile& tile, uint32_t c0, const fe_t* tws = nullptr) {
     constexpr uint32_t R = 1u << S;
     const uint32_t T = blockDim.x, tid = threadIdx.x;
     const uint32_t log_c = A.log_c, cmask = (1u << log_c) - 1;
     const uint32_t log_cols = A.log_n - S;  // columns = n / R
-    uint32_t i = 0;
+    uint32_t i = 0, tw_off = 0;
 #pragma unroll 1
     for (; i + 1 < S; i += 2) {
         const uint32_t log_q = S - 2 - i, q = 1u << log_q;
+        const fe_t* tw_round = TWS ? tws + tw_off : nullptr;
+        tw_off += 3u << log_q;
         for (uint32_t g = tid; g < ((R / 4) << log_c); g += T) {
             const uint32_t c = g & cmask, gf = g >> log_c;
             const uint32_t blk = gf >> log_q, rp = gf & (q - 1);
@@ -141,10 +145,10 @@ __device__ __forceinline__ void ntt_tile_stages(const NttPassArgs& A, const Tile
             const fe_t a0 = tile.ld(i0), a1 = tile.ld(i0 + st), a2 = tile.ld(i0 + 2 * st), a3 = tile.ld(i0 + 3 * st);
             const fe_t u0 = Fr::add(a0, a2), u1 = Fr::add(a1, a3);
             fe_t d0 = Fr::sub(a0, a2), d1 = Fr::sub(a1, a3);
-            if (ea) d0 = Fr::mul(d0, ld_fe_nc(A.tw + ea));
+            if (ea) d0 = Fr::mul(d0, TWS ? ld_fe(tw_round + rp) : ld_fe_nc(A.tw + ea));
             // zero-padded first pass (coeff_to_extended: 3/4 of the rows are zero): a1 = a3 = 0 in the first round, 0 * w = 0
-            if (!Fr::is_zero(d1)) d1 = Fr::mul(d1, ld_fe_nc(A.tw + eb));
-            const fe_t wc = ld_fe_nc(A.tw + ec);
+            if (!Fr::is_zero(d1)) d1 = Fr::mul(d1, TWS ? ld_fe(tw_round + rp + q) : ld_fe_nc(A.tw + eb));
+            const fe_t wc = TWS ? ld_fe(tw_round + 2 * q + rp) : ld_fe_nc(A.tw + ec);
             tile.st(i0, Fr::add(u0, u1));
             tile.st(i0 + 2 * st, Fr::add(d0, d1));
             fe_t v1 = Fr::sub(u0, u1), v3 = Fr::sub(d0, d1);
@@ -202,13 +206,37 @@ __device__ __forceinline__ void ntt_tile_store(const NttPassArgs& A, const Tile&
     }
 }
 
+// Twiddles of one pass behind the first (log_c <= log_s: all columns of the CTA share base = s * p'): about R values,
+// fetched once per CTA next to the tile load instead of three 32-byte L2 / L1 reads per radix-4 unit and round.
 template <int S>
+__device__ __forceinline__ void ntt_stage_twiddles(const NttPassArgs& A, uint32_t c0, fe_t* tws) {
+    const uint32_t log_cols = A.log_n - S;
+    const uint32_t base = (c0 >> A.log_s) << A.log_s;
+    uint32_t off = 0;
+    for (uint32_t i = 0; i + 1 < (uint32_t)S; i += 2) {
+        const uint32_t q = 1u << (S - 2 - i);
+        for (uint32_t j = threadIdx.x; j < 3 * q; j += blockDim.x) {
+            const uint32_t e = j < 2 * q ? (base + (j << log_cols)) << i : ((base + ((j - 2 * q) << log_cols)) << i) << 1;
+            st_fe(tws + off + j, ld_fe_nc(A.tw + e));
+        }
+        off += 3 * q;
+    }
+}
+template <int S>
+constexpr uint32_t ntt_staged_twiddles() {   // entries ntt_stage_twiddles writes
+    uint32_t n = 0;
+    for (int i = 0; i + 1 < S; i += 2) n += 3u << (S - 2 - i);
+    return n;
+}
+
+template <int S, bool TWS>
 __global__ void __launch_bounds__(256, 4) k_ntt_pass(const NttPassArgs A) {
     constexpr uint32_t R = 1u << S;
     extern __shared__ uint4 smem_raw[];
     SplitTile tile;
     tile.lo = smem_raw;
     tile.hi = smem_raw + ((size_t)(1u << S) << A.log_c);
+    fe_t* tws = reinterpret_cast<fe_t*>(smem_raw + ((size_t)(2u << S) << A.log_c));
     const uint32_t T = blockDim.x, tid = threadIdx.x;
     const uint32_t log_c = A.log_c, cmask = (1u << log_c) - 1;
     const uint32_t log_cols = A.log_n - S;  // columns = n / R
@@ -233,8 +261,9 @@ __global__ void __launch_bounds__(256, 4) k_ntt_pass(const NttPassArgs A) {
         }
         tile.st(idx, v);
     }
+    if (TWS) ntt_stage_twiddles<S>(A, c0, tws);
     __syncthreads();
-    ntt_tile_stages<S>(A, tile, c0);
+    ntt_tile_stages<S, SplitTile, TWS>(A, tile, c0, tws);
     ntt_tile_store<S>(A, tile, c0, y);
 }
 
@@ -339,19 +368,24 @@ static encode_tiled_fn get_encode_tiled() {
     }();
     return fn;
 }
-static ntt_kernel_t pass_kernel(int S) {
+static ntt_kernel_t pass_kernel(int S, bool tws) {
     switch (S) {
-        case 1: return k_ntt_pass<1>;
-        case 2: return k_ntt_pass<2>;
-        case 3: return k_ntt_pass<3>;
-        case 4: return k_ntt_pass<4>;
-        case 5: return k_ntt_pass<5>;
-        case 6: return k_ntt_pass<6>;
-        case 7: return k_ntt_pass<7>;
-        case 8: return k_ntt_pass<8>;
-        case 9: return k_ntt_pass<9>;
+        case 1: return k_ntt_pass<1, false>;
+        case 2: return tws ? k_ntt_pass<2, true> : k_ntt_pass<2, false>;
+        case 3: return tws ? k_ntt_pass<3, true> : k_ntt_pass<3, false>;
+        case 4: return tws ? k_ntt_pass<4, true> : k_ntt_pass<4, false>;
+        case 5: return tws ? k_ntt_pass<5, true> : k_ntt_pass<5, false>;
+        case 6: return tws ? k_ntt_pass<6, true> : k_ntt_pass<6, false>;
+        case 7: return tws ? k_ntt_pass<7, true> : k_ntt_pass<7, false>;
+        case 8: return tws ? k_ntt_pass<8, true> : k_ntt_pass<8, false>;
+        case 9: return tws ? k_ntt_pass<9, true> : k_ntt_pass<9, false>;
         default: return nullptr;
     }
+}
+static uint32_t staged_twiddles(int S) {
+    uint32_t n = 0;
+    for (int i = 0; i + 1 < S; i += 2) n += 3u << (S - 2 - i);
+    return n;
 }
 
 int32_t ntt_get_twiddles(b2r_ctx* ctx, const fe_t& omega, uint32_t log_n, const fe_t** out) {
@@ -502,7 +536,14 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         if (p > 0 && log_c > log_s) log_c = log_s;
         A.log_c = log_c;
         size_t smem = ((size_t)sizeof(fe_t) << S[p]) << log_c;
-        ntt_kernel_t kern = pass_kernel(S[p]);
+        // passes behind the first: the CTA's columns share their twiddles (log_c <= log_s) and can stage them in shared memory
+        // once.  Opt-in ("1"): measured 3 % SLOWER on B200 (64 x 2^19: 5.79 vs 5.64 ms) - at the 64-register cap of 4 CTAs/SM
+        // the extra addressing spills (92 vs 36 bytes), and 32 warps per SM already hide the L1-resident twiddle reads
+        bool tws = false;
+        if (const char* ov = getenv("B2R_NTT_TWS")) tws = ov[0] == '1' && p > 0 && S[p] >= 2 && log_c <= log_s;
+        const size_t tile_smem = smem;
+        if (tws) smem += (size_t)staged_twiddles(S[p]) * sizeof(fe_t);
+        ntt_kernel_t kern = pass_kernel(S[p], tws);
         if (smem > 48 * 1024) B2R_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // TMA path: tiles of at most 32 KiB (two ring stages, 3 CTAs per SM), at least one 128-byte line per row, rows <= 256
         bool use_tma = false;
@@ -513,7 +554,7 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
             const bool want = ov && ov[0] == '1';
             const uint32_t ncols = 1u << log_cols;
             const uint32_t vec_rows = (uint32_t)((src_len + ncols - 1) / ncols);   // rows that exist in memory (rest: zero fill)
-            use_tma = want && get_encode_tiled() && pass_kernel_tma(S[p]) && log_c >= 2 && smem <= 32 * 1024 && vec_rows >= 1 &&
+            use_tma = want && get_encode_tiled() && pass_kernel_tma(S[p]) && log_c >= 2 && tile_smem <= 32 * 1024 && vec_rows >= 1 &&
                       (src_len % ncols == 0) && (src_stride % 4 == 0) && ((uintptr_t)src % 16 == 0);
             if (use_tma) {
                 const uint32_t inner = A.in_inner ? A.in_inner : (uint32_t)batch, outer = A.in_inner ? (uint32_t)(batch / A.in_inner) : 1u;
@@ -532,8 +573,8 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
                     M.tiles_per_vec = 1u << (log_cols - log_c);
                     M.total_tiles = M.tiles_per_vec * (uint32_t)batch;
                     M.inner = inner;
-                    M.tile_bytes = (uint32_t)smem;
-                    const size_t dyn = 2 * smem + 1024;
+                    M.tile_bytes = (uint32_t)tile_smem;
+                    const size_t dyn = 2 * tile_smem + 1024;
                     ntt_tma_kernel_t tk = pass_kernel_tma(S[p]);
                     B2R_CUDA(ctx, cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
                     const uint32_t resident = 3u * (uint32_t)ctx->sm_count;

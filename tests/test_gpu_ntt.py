@@ -145,4 +145,11 @@ def test_tma_tile_loader_matches_plain_loads(ctx, monkeypatch, log_n, batch):
     tma = run()
     for x, y in zip(base, tma):
         assert (x is None and y is None) or np.array_equal(x, y)
+    # the other opt-in variant: twiddles of the passes behind the first staged in shared memory (B2R_NTT_TWS=1)
+    monkeypatch.setenv("B2R_NTT_TMA", "0")
+    monkeypatch.setenv("B2R_NTT_TWS", "1")
+    tws = run()
+    monkeypatch.delenv("B2R_NTT_TWS")
+    for x, y in zip(base, tws):
+        assert (x is None and y is None) or np.array_equal(x, y)
     assert np.array_equal(base[1].view(np.uint64).reshape(-1, 4), a)     # the inverse undoes the forward transform
