@@ -25,6 +25,12 @@
 #define B2R_D inline
 #endif
 
+// 1 = Fr's m * p rows without a multiplier for the low word (below): bit-exact, measured SLOWER on B200 (NTT passes 159 ->
+// 177 ms, quotient 56 -> 66 ms per step: the passes are as short of ALU / issue slots as of multiplier cycles), default off
+#ifndef B2R_SPARSE_P0
+#define B2R_SPARSE_P0 0
+#endif
+
 namespace b2r {
 
 struct alignas(16) fe_t {
@@ -319,6 +325,55 @@ struct Field {
         return r;
     }
 
+    // ---- the m * p rows -------------------------------------------------------------------------------------
+    // m = -t0 / p mod 2^32.  Fr's modulus ends in 0xf0000001 = 2^32 - 2^28 + 1, so n0' = 0xefffffff = -(2^28 + 1) and
+    // m = -(t0 + (t0 << 28)): two ALU operations instead of a multiply on the (binding) fma pipe.
+    static constexpr bool SPARSE_P0 = B2R_SPARSE_P0 && P::MOD(0) == 0xf0000001u;
+    B2R_HD static uint32_t mont_m(uint32_t t0) {
+        if constexpr (SPARSE_P0) return 0u - t0 - (t0 << 28);
+        else return t0 * P::N0INV;
+    }
+    // X[0..7] += lanes (p0, p2, p4, p6) * mi, returns the carry out of word 7.  X[0] + lo(p0 * mi) is 0 mod 2^32 by the
+    // choice of mi and never read again, so for Fr the first lane needs no multiplier: the carry into word 1 is
+    // (X[0] != 0) and hi(mi * (2^32 - 2^28 + 1)) = mi - ceil(mi (2^28 - 1) / 2^32) comes from shifts and subtractions -
+    // one wide MAD per row (8 of the 128 of a product) moved to the ALU pipe.  X[0] is left stale.
+    B2R_HD static uint32_t mod_row_even(uint32_t* X, const uint32_t* m, uint32_t mi) {
+        if constexpr (!SPARSE_P0) {
+            return row_mad(X, m, mi);
+        } else {
+            uint32_t c;
+#if defined(__CUDA_ARCH__)
+            uint32_t ylo, yhi;
+            asm("sub.cc.u32 %0, %2, %3; subc.u32 %1, %4, 0;" : "=r"(ylo), "=r"(yhi) : "r"(mi << 28), "r"(mi), "r"(mi >> 4));
+            const uint32_t h = mi - yhi - (ylo != 0u ? 1u : 0u);
+            asm("add.cc.u32 %7, %8, 0xffffffff;"
+                "addc.cc.u32 %0, %0, %9;"
+                "madc.lo.cc.u32 %1, %10, %13, %1; madc.hi.cc.u32 %2, %10, %13, %2;"
+                "madc.lo.cc.u32 %3, %11, %13, %3; madc.hi.cc.u32 %4, %11, %13, %4;"
+                "madc.lo.cc.u32 %5, %12, %13, %5; madc.hi.cc.u32 %6, %12, %13, %6;"
+                "addc.u32 %7, 0, 0;"
+                : "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "=&r"(c)
+                : "r"(X[0]), "r"(h), "r"(m[2]), "r"(m[4]), "r"(m[6]), "r"(mi));
+#else
+            const uint64_t y = ((uint64_t)mi << 28) - mi;   // mi (2^28 - 1)
+            const uint32_t h = mi - (uint32_t)(y >> 32) - ((uint32_t)y != 0u ? 1u : 0u);
+            uint64_t cy = X[0] != 0u ? 1u : 0u;
+            uint64_t t1 = (uint64_t)X[1] + h + cy;
+            X[1] = (uint32_t)t1;
+            cy = t1 >> 32;
+            for (int l = 1; l < 4; l++) {
+                uint64_t x = (uint64_t)X[2 * l] | ((uint64_t)X[2 * l + 1] << 32);
+                unsigned __int128 t = (unsigned __int128)m[2 * l] * mi + x + cy;
+                X[2 * l] = (uint32_t)t;
+                X[2 * l + 1] = (uint32_t)(t >> 32);
+                cy = (uint64_t)(t >> 64);
+            }
+            c = (uint32_t)cy;
+#endif
+            return c;
+        }
+    }
+
     // Montgomery product a*b*R^-1 mod p, inputs and output fully reduced (< p).
     // Invariant per iteration (T = Pw + 2^32 * Sw): T < a + p < 2^255 at iteration start,
     // so the S chains never carry out of 8 words and Pw needs one carry word (<= 2).
@@ -329,8 +384,8 @@ struct Field {
         // i = 0
         row_mul(Pw, &a.l[0], b.l[0]);
         row_mul(Sw, &a.l[1], b.l[0]);
-        uint32_t mi = Pw[0] * P::N0INV;
-        Pw[8] = row_mad(Pw, &m[0], mi);
+        uint32_t mi = mont_m(Pw[0]);
+        Pw[8] = mod_row_even(Pw, &m[0], mi);
         row_mad_nc(Sw, &m[1], mi);
 #pragma unroll
         for (int i = 1; i < 8; i++) {
@@ -340,8 +395,8 @@ struct Field {
             for (int k = 0; k < 8; k++) nS[k] = Pw[k + 2];
             for (int k = 0; k < 8; k++) nP[k] = Sw[k];
             nP[8] = row_mad(nP, &a.l[0], b.l[i]);
-            mi = nP[0] * P::N0INV;
-            nP[8] += row_mad(nP, &m[0], mi);
+            mi = mont_m(nP[0]);
+            nP[8] += mod_row_even(nP, &m[0], mi);
             row_mad_nc(nS, &m[1], mi);
             for (int k = 0; k < 9; k++) Pw[k] = nP[k];
             for (int k = 0; k < 8; k++) Sw[k] = nS[k];
@@ -366,8 +421,8 @@ struct Field {
         row_mul(Sw, &a.l[1], b.l[0]);
         Pw[8] = row_mad(Pw, &c.l[0], d.l[0]);
         row_mad_nc(Sw, &c.l[1], d.l[0]);
-        uint32_t mi = Pw[0] * P::N0INV;
-        Pw[8] += row_mad(Pw, &m[0], mi);
+        uint32_t mi = mont_m(Pw[0]);
+        Pw[8] += mod_row_even(Pw, &m[0], mi);
         row_mad_nc(Sw, &m[1], mi);
 #pragma unroll
         for (int i = 1; i < 8; i++) {
@@ -378,8 +433,8 @@ struct Field {
             nP[8] = row_mad(nP, &a.l[0], b.l[i]);
             nP[8] += row_mad(nP, &c.l[0], d.l[i]);
             row_mad_nc(nS, &c.l[1], d.l[i]);
-            mi = nP[0] * P::N0INV;
-            nP[8] += row_mad(nP, &m[0], mi);
+            mi = mont_m(nP[0]);
+            nP[8] += mod_row_even(nP, &m[0], mi);
             row_mad_nc(nS, &m[1], mi);
             for (int k = 0; k < 9; k++) Pw[k] = nP[k];
             for (int k = 0; k < 8; k++) Sw[k] = nS[k];
@@ -412,8 +467,8 @@ struct Field {
         row_mad_nc(Sw, &a2.l[1], b2.l[0]);
         Pw[8] += row_mad(Pw, &a3.l[0], b3.l[0]);
         row_mad_nc(Sw, &a3.l[1], b3.l[0]);
-        uint32_t mi = Pw[0] * P::N0INV;
-        Pw[8] += row_mad(Pw, &m[0], mi);
+        uint32_t mi = mont_m(Pw[0]);
+        Pw[8] += mod_row_even(Pw, &m[0], mi);
         row_mad_nc(Sw, &m[1], mi);
 #pragma unroll
         for (int i = 1; i < 8; i++) {
@@ -428,8 +483,8 @@ struct Field {
             row_mad_nc(nS, &a2.l[1], b2.l[i]);
             nP[8] += row_mad(nP, &a3.l[0], b3.l[i]);
             row_mad_nc(nS, &a3.l[1], b3.l[i]);
-            mi = nP[0] * P::N0INV;
-            nP[8] += row_mad(nP, &m[0], mi);
+            mi = mont_m(nP[0]);
+            nP[8] += mod_row_even(nP, &m[0], mi);
             row_mad_nc(nS, &m[1], mi);
             for (int k = 0; k < 9; k++) Pw[k] = nP[k];
             for (int k = 0; k < 8; k++) Sw[k] = nS[k];
@@ -442,13 +497,13 @@ struct Field {
     // iteration I >= 1 of sqr(): shift fused with the odd lanes of m * p, even lanes of m * p, then row I of the square
     template <int I>
     B2R_HD static void sqr_step(uint32_t* Pw, uint32_t* Sw, const uint32_t* a, const uint32_t* D, const uint32_t* m) {
-        const uint32_t mi = (Sw[0] + Pw[1]) * P::N0INV;
+        const uint32_t mi = mont_m(Sw[0] + Pw[1]);
         row_shift_mad(Pw, &Sw[0], &m[1], mi);
         uint32_t nP[10], nS[10];
         for (int k = 0; k < 8; k++) nS[k] = Pw[k + 2];
         for (int k = 0; k < 8; k++) nP[k] = Sw[k];
         nS[8] = 0;
-        nP[8] = row_mad(nP, &m[0], mi);
+        nP[8] = mod_row_even(nP, &m[0], mi);
         uint32_t V[9];
         for (int k = 0; k < 8; k++) V[k] = D[k];
         V[8] = 0;
@@ -482,8 +537,8 @@ struct Field {
             row_mul(Pw, &V[0], a.l[0]);
             row_mul(Sw, &V[1], a.l[0]);
         }
-        uint32_t mi = Pw[0] * P::N0INV;
-        Pw[8] = row_mad(Pw, &m[0], mi);
+        uint32_t mi = mont_m(Pw[0]);
+        Pw[8] = mod_row_even(Pw, &m[0], mi);
         row_mad_nc(Sw, &m[1], mi);
         sqr_step<1>(Pw, Sw, a.l, D, m);
         sqr_step<2>(Pw, Sw, a.l, D, m);

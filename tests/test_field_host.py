@@ -11,10 +11,14 @@ import bn254 as O
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def test_field_cuh_host_build_matches_python():
+import pytest
+
+
+@pytest.mark.parametrize("sparse_p0", [0, 1])   # 1: the opt-in Fr reduction rows without a multiplier for the low word
+def test_field_cuh_host_build_matches_python(sparse_p0):
     with tempfile.TemporaryDirectory() as d:
         exe = os.path.join(d, "fht")
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(HERE, "host", "field_host_test.cpp")])
+        subprocess.check_call(["g++", "-O1", "-std=c++17", f"-DB2R_SPARSE_P0={sparse_p0}", "-o", exe, os.path.join(HERE, "host", "field_host_test.cpp")])
         out = subprocess.check_output([exe, "600"], text=True)
     R = O.MONT_R
     n = 0
