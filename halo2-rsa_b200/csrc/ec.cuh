@@ -136,6 +136,16 @@ B2R_HD void xyzz_add(xyzz_t& acc, const xyzz_t& q) {
     acc.zzz = Fq::mul(Fq::mul(acc.zzz, q.zzz), PPP);
 }
 
+// The P + P case of the lock-step mixed addition is taken about once per 2^254 random operands (and for repeated table
+// points), but its doubling is 7 field products of straight-line code inside the hot loop: 20 of the 65 KB of
+// k_accum_entries.  Out of line on the device: the loop shrinks (accumulation 221.8 -> 219.7 ms per step), the rare call
+// pays the ABI's argument copies.  (The same for the full addition made k_br_level1 slower: caller-saved spills.)
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ xyzz_t xyzz_double_affine_ool(affine_t p) { return xyzz_double_affine(p); }
+#else
+inline xyzz_t xyzz_double_affine_ool(affine_t p) { return xyzz_double_affine(p); }
+#endif
+
 // ---- lock-step variants -----------------------------------------------------------------------
 // Same results as xyzz_madd / xyzz_add, written so that all lanes of a warp execute the same
 // instruction stream: the general formulas run unconditionally and the identity cases are
@@ -174,7 +184,7 @@ B2R_HD void xyzz_madd_ls(xyzz_t& acc, const affine_t& q, bool neg) {
             affine_t t;
             t.x = q.x;
             t.y = qy;
-            acc = xyzz_double_affine(t);
+            acc = xyzz_double_affine_ool(t);
         } else {
             acc = xyzz_identity();
         }
