@@ -1116,7 +1116,8 @@ static int32_t msm_group(b2r_ctx* ctx, const b2r_bases* bs, const fe_t* scalars_
         else k_accum_entries<MSM_L1, MINB, PF><<<ga, 128, 0, st>>>(bs->table, ent, key, ent_cap, off, B, nch1, bk, ka, pa, slotsA);           \
     } while (0)
         // measured on B200 (64 x 2^17 uniform scalars, tools/microbench.py): 4 CTAs/SM without the point prefetch 22.7 ms,
-        // with it 24.1 ms (spills); 5 or 6 CTAs/SM (96 / 80 registers, spills) 23.5 - 24.0 ms
+        // with it 24.1 ms (spills); 5 or 6 CTAs/SM (96 / 80 registers, spills) 23.5 - 24.0 ms.  Re-measured on the in-place
+        // 1160-MAD addition (bench.py, accumulation ms per step): 4 CTAs 220.1, 5 CTAs (96 registers, 40 bytes of spills) 220.1
         switch (variant) {
             case 1: B2R_ACC(4, true); break;
             case 3:   // table points staged through a shared-memory ring by per-lane cp.async.bulk + mbarrier
