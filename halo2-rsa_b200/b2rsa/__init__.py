@@ -83,6 +83,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_rsa_prove_batch_dev": [vp, vp, vp, vp, vp, sz, u64, vp, vp],
         "b2r_rsa_prove_batch_ex": [vp, vp, vp, vp, vp, sz, vp, u64, u32, vp, vp],
         "b2r_pk_set_transcript_repr": [vp, vp],
+        "b2r_field_selftest": [vp, u32, u32, vp, vp, vp, vp, vp, sz],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the ABI symbol is missing: loud by design
@@ -254,6 +255,18 @@ class Context:
             self._ck(self.lib.b2r_msm_g1_batch_dev_ex(self.h, bases.h, C.c_void_p(scalars_dptr), m, n, self.MSM_UNIFORM, C.c_void_p(out_dptr)))
         else:
             self._ck(self.lib.b2r_msm_g1_batch_dev(self.h, bases.h, C.c_void_p(scalars_dptr), m, n, C.c_void_p(out_dptr)))
+
+    FIELD_OPS = {"mul": 0, "sqr": 1, "mul_add_mul": 2, "mul_sub_mul": 3, "dot4": 4, "add": 5, "sub": 6, "inv": 7}
+
+    def field_selftest(self, field: str, op: str, a, b=None, c=None, d=None) -> np.ndarray:
+        """diagnostic: the device field arithmetic (csrc/field.cuh) on uint64[n,4] Montgomery operands"""
+        a = _fr_array(a)
+        ops = [None if x is None else _fr_array(x) for x in (b, c, d)]
+        out = np.empty_like(a)
+        ptr = lambda x: C.c_void_p(None) if x is None else _host_ptr(x)
+        self._ck(self.lib.b2r_field_selftest(self.h, {"fr": 0, "fq": 1}[field], self.FIELD_OPS[op], _host_ptr(a), ptr(ops[0]), ptr(ops[1]),
+                                             ptr(ops[2]), _host_ptr(out), a.shape[0]))
+        return out
 
     def srs_setup(self, k: int, secret: np.ndarray):
         """ParamsKZG::setup(k) for a chosen secret (uint64[4] Montgomery) -> (g, g_lagrange)"""

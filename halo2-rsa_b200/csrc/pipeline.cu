@@ -56,6 +56,26 @@ __global__ void __launch_bounds__(128) k_srs_points(affine_t* out, fe_t s, fe_t 
     }
     out[i] = g1_mul_generator(sc);
 }
+
+// b2r_field_selftest: one field operation per thread on caller-supplied operands
+template <class F>
+__global__ void __launch_bounds__(128) k_field_selftest(uint32_t op, const fe_t* a, const fe_t* b, const fe_t* c, const fe_t* d, fe_t* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fe_t x = a[i], y = b ? b[i] : F::zero(), z = c ? c[i] : F::zero(), w = d ? d[i] : F::zero();
+    fe_t r = F::zero();
+    switch (op) {
+        case 0: r = F::mul(x, y); break;
+        case 1: r = F::sqr(x); break;
+        case 2: r = F::mul_add_mul(x, y, z, w); break;
+        case 3: r = F::mul_sub_mul(x, y, z, w); break;
+        case 4: r = F::dot4(x, y, z, w, x, z, y, w); break;
+        case 5: r = F::add(x, y); break;
+        case 6: r = F::sub(x, y); break;
+        case 7: r = F::inv_vartime(x); break;
+    }
+    out[i] = r;
+}
 }  // namespace b2r
 
 using namespace b2r;
@@ -136,6 +156,33 @@ int32_t b2r_rsa_commit_batch(b2r_ctx* ctx, const b2r_prog* prog, const b2r_bases
     B2R_TRY(b2r_rsa_commit_batch_dev(ctx, prog, g_lagrange, d_n, d_s, d_h, batch, blind_seed, k, ext_k, advice_dev, ext_dev, d_cm, d_valid));
     B2R_CUDA(ctx, cudaMemcpyAsync(commitments, d_cm, batch * 5 * sizeof(b2r_g1_affine), cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaMemcpyAsync(is_valid, d_valid, batch, cudaMemcpyDeviceToHost, ctx->stream));
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+} B2R_ABI_CATCH(ctx)
+
+
+int32_t b2r_field_selftest(b2r_ctx* ctx, uint32_t field, uint32_t op, const b2r_fr* a, const b2r_fr* b, const b2r_fr* c,
+                           const b2r_fr* d, b2r_fr* out, size_t n) try {
+    B2R_ENTER(ctx);
+    if (!a || !out || field > 1 || op > 7) return fail(ctx, B2R_ERR_INVALID, "field_selftest: bad argument");
+    const bool need_b = op == 0 || (op >= 2 && op <= 6), need_cd = op >= 2 && op <= 4;
+    if ((need_b && !b) || (need_cd && (!c || !d))) return fail(ctx, B2R_ERR_INVALID, "field_selftest: operand missing");
+    if (n == 0) return 0;
+    fe_t* buf = nullptr;
+    B2R_TRY(scratch_get(ctx, SC_STAGE, 5 * n * sizeof(fe_t), (void**)&buf));
+    const b2r_fr* src[4] = {a, need_b ? b : nullptr, need_cd ? c : nullptr, need_cd ? d : nullptr};
+    fe_t* dev[4] = {buf, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4; k++) {
+        if (!src[k]) continue;
+        dev[k] = buf + (size_t)k * n;
+        B2R_CUDA(ctx, cudaMemcpyAsync(dev[k], src[k], n * sizeof(fe_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    fe_t* o = buf + 4 * n;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (field == 0) k_field_selftest<Fr><<<grid, 128, 0, ctx->stream>>>(op, dev[0], dev[1], dev[2], dev[3], o, n);
+    else k_field_selftest<Fq><<<grid, 128, 0, ctx->stream>>>(op, dev[0], dev[1], dev[2], dev[3], o, n);
+    B2R_LAUNCH_CHECK(ctx);
+    B2R_CUDA(ctx, cudaMemcpyAsync(out, o, n * sizeof(fe_t), cudaMemcpyDeviceToHost, ctx->stream));
     B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 } B2R_ABI_CATCH(ctx)

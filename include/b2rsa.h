@@ -69,6 +69,14 @@ int32_t b2r_profile_enable(b2r_ctx* ctx, int32_t on);
 int32_t b2r_profile_read(b2r_ctx* ctx, const char* name, double* total_ms, uint64_t* launches, double* units);
 int32_t b2r_profile_dump(b2r_ctx* ctx, char* buf, size_t cap, int32_t clear);
 
+/* Diagnostic: the device field arithmetic on caller-supplied operands, one thread per element (host buffers of n
+ * elements in halo2curves' memory format, i.e. Montgomery limbs; operands must be < p).  field: 0 = Fr, 1 = Fq (the
+ * arithmetic under halo2curves' bn256::{Fr, Fq}: Mul / Square / Add / Sub / invert).  op: 0 a*b, 1 a^2, 2 a*b + c*d,
+ * 3 a*b - c*d, 4 a*b + c*d + a*c + b*d (the sums with ONE reduction the kernels use), 5 a + b, 6 a - b, 7 a^-1 (0 -> 0).
+ * c, d may be NULL for ops that do not read them.  Used by tests/test_gpu_field.py against Python integers. */
+int32_t b2r_field_selftest(b2r_ctx* ctx, uint32_t field, uint32_t op, const b2r_fr* a, const b2r_fr* b, const b2r_fr* c,
+                           const b2r_fr* d, b2r_fr* out, size_t n);
+
 /* plain device memory helpers so a host language needs no CUDA binding of its own */
 int32_t b2r_dev_alloc(b2r_ctx* ctx, size_t bytes, void** dptr);
 int32_t b2r_dev_free(b2r_ctx* ctx, void* dptr);

@@ -66,6 +66,8 @@ extern "C" {
     pub fn b2r_pk_info(pk: *const b2r_pk, k: *mut u32, ext_k: *mut u32, num_fixed: *mut u32, num_sigma: *mut u32, proof_bytes: *mut u64) -> i32;
     pub fn b2r_pk_export_vk(pk: *const b2r_pk, fixed: *mut G1Affine, sigma: *mut G1Affine, transcript_repr: *mut Fr) -> i32;
     pub fn b2r_pk_set_transcript_repr(pk: *mut b2r_pk, transcript_repr: *const Fr) -> i32;
+    // diagnostic: device field arithmetic on host operands (field 0 = Fr, 1 = Fq; see include/b2rsa.h for the op codes)
+    pub fn b2r_field_selftest(ctx: *mut b2r_ctx, field: u32, op: u32, a: *const Fr, b: *const Fr, c: *const Fr, d: *const Fr, out: *mut Fr, n: usize) -> i32;
     pub fn b2r_rsa_prove_batch(ctx: *mut b2r_ctx, pk: *const b2r_pk, n_limbs: *const u64, sig_limbs: *const u64, hash_limbs: *const u64,
                                batch: usize, seed: u64, proofs: *mut u8, status: *mut u8) -> i32;
     pub fn b2r_rsa_prove_batch_ex(ctx: *mut b2r_ctx, pk: *const b2r_pk, n_limbs: *const u64, sig_limbs: *const u64, hash_limbs: *const u64,
