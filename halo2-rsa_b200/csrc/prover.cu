@@ -541,18 +541,38 @@ __device__ __forceinline__ fe_t fr_pow_u32(fe_t a, uint32_t e) {
     }
     return acc;
 }
-// evals[p][e] = poly_e(point_e): thread t sums coefficients t, t + 256, ... by Horner in z^256, times z^t, block tree sum
+// evals[p][e] = poly_e(point_e).  Thread t sums coefficients t, t + 256, ...: S_t = sum_j c[256 j + t] w^j with w = z^256, then
+// S_t z^t and a block tree sum.  The powers w^j (at most 512 of them, 16 KB) are built once per CTA in shared memory, so the
+// inner sum is a dot product taken four terms per Montgomery reduction (Fr::dot4: 80 instead of the 128 wide MADs per
+// coefficient of a Horner step); blocks of 512 powers are chained by Horner in w^512 for larger n.
+static constexpr uint32_t EVAL_WB = 512;
 __global__ void __launch_bounds__(256)
 k_eval(const PolyTable T, const EvalPlan* __restrict__ plan, const fe_t* __restrict__ points /* [B][NPOINTS] */, fe_t* __restrict__ evals) {
     __shared__ uint4 smem_raw[256 * 2];
+    __shared__ uint4 pw_raw[EVAL_WB * 2];
     fe_t* sh = reinterpret_cast<fe_t*>(smem_raw);
+    fe_t* W = reinterpret_cast<fe_t*>(pw_raw);
     const uint32_t e = blockIdx.x, p = blockIdx.y, t = threadIdx.x;
     const fe_t* c = poly_ptr(T, plan->poly[e], p);
     const fe_t z = ldv(points + (size_t)p * NPOINTS + plan->point[e]);
     fe_t w = z;
     for (int i = 0; i < 8; i++) w = Fr::sqr(w);  // z^256
+    const uint32_t m = T.n / 256;                // coefficients per thread
+    const uint32_t wb = m < EVAL_WB ? m : EVAL_WB;
+    for (uint32_t j = t; j < wb; j += 256) stv(W + j, fr_pow_u32(w, j));
+    const fe_t w_blk = fr_pow_u32(w, wb);
+    __syncthreads();
     fe_t acc = Fr::zero();
-    for (int j = (int)(T.n / 256) - 1; j >= 0; j--) acc = Fr::add(Fr::mul(acc, w), ldv(c + (size_t)j * 256 + t));
+    for (int blk = (int)(m / wb) - 1; blk >= 0; blk--) {
+        const fe_t* cb = c + (size_t)blk * wb * 256 + t;
+        fe_t s = Fr::zero();
+        uint32_t j = 0;
+        for (; j + 4 <= wb; j += 4)
+            s = Fr::add(s, Fr::dot4(ldv(cb + (size_t)j * 256), ldv(W + j), ldv(cb + (size_t)(j + 1) * 256), ldv(W + j + 1),
+                                    ldv(cb + (size_t)(j + 2) * 256), ldv(W + j + 2), ldv(cb + (size_t)(j + 3) * 256), ldv(W + j + 3)));
+        for (; j < wb; j++) s = Fr::add(s, Fr::mul(ldv(cb + (size_t)j * 256), ldv(W + j)));
+        acc = Fr::add(Fr::mul(acc, w_blk), s);
+    }
     acc = Fr::mul(acc, fr_pow_u32(z, t));
     stv(sh + t, acc);
     __syncthreads();
