@@ -586,19 +586,28 @@ struct LincombPlan {
     PolyRef poly[NPOINTS][MAXTERMS];
     uint32_t nterms[NPOINTS];
 };
-// out[p][g][row] = sum_j scal[p][g][j] * poly_{g,j}[row]
+// out[p][g][row] = sum_j scal[p][g][j] * poly_{g,j}[row].  The scalars and polynomial base pointers of the (proof, point)
+// pair are staged in shared memory once per CTA (the inner loop then has no dependent global loads for them), and the sum
+// takes four terms per Montgomery reduction.
 __global__ void __launch_bounds__(256)
 k_lincomb(const PolyTable T, const LincombPlan* __restrict__ plan, const fe_t* __restrict__ scal /* [B][NPOINTS][MAXTERMS] */, fe_t* __restrict__ out) {
+    __shared__ uint4 sc_raw[MAXTERMS * 2];
+    __shared__ const fe_t* base[MAXTERMS];
+    fe_t* sc = reinterpret_cast<fe_t*>(sc_raw);
     const uint32_t g = blockIdx.y, p = blockIdx.z, row = blockIdx.x * 256 + threadIdx.x;
-    if (row >= T.n) return;
     const uint32_t m = plan->nterms[g];
-    const fe_t* sc = scal + ((size_t)p * NPOINTS + g) * MAXTERMS;
-    auto term = [&](uint32_t j) { return ldv(poly_ptr(T, plan->poly[g][j], p) + row); };
+    if (threadIdx.x < m) {
+        stv(sc + threadIdx.x, ldv_nc(scal + ((size_t)p * NPOINTS + g) * MAXTERMS + threadIdx.x));
+        base[threadIdx.x] = poly_ptr(T, plan->poly[g][threadIdx.x], p);
+    }
+    __syncthreads();
+    if (row >= T.n) return;
+    auto term = [&](uint32_t j) { return ldv(base[j] + row); };
     fe_t acc = Fr::zero();
     uint32_t j = 0;
     for (; j + 4 <= m; j += 4)   // four terms per Montgomery reduction
-        acc = Fr::add(acc, Fr::dot4(ldv_nc(sc + j), term(j), ldv_nc(sc + j + 1), term(j + 1), ldv_nc(sc + j + 2), term(j + 2), ldv_nc(sc + j + 3), term(j + 3)));
-    for (; j < m; j++) acc = Fr::add(acc, Fr::mul(ldv_nc(sc + j), term(j)));
+        acc = Fr::add(acc, Fr::dot4(ldv(sc + j), term(j), ldv(sc + j + 1), term(j + 1), ldv(sc + j + 2), term(j + 2), ldv(sc + j + 3), term(j + 3)));
+    for (; j < m; j++) acc = Fr::add(acc, Fr::mul(ldv(sc + j), term(j)));
     stv(out + ((size_t)p * NPOINTS + g) * T.n + row, acc);
 }
 // q = (f(X) - f(z)) / (X - z): q_{i-1} = c_i + z q_i.  One CTA per polynomial; thread = n/256 consecutive coefficients:
