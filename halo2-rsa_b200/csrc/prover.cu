@@ -279,15 +279,22 @@ __global__ void __launch_bounds__(256)
 k_perm_numden(const fe_t* __restrict__ P, const fe_t* __restrict__ sigma_values, const fe_t* __restrict__ tw, const fe_t* __restrict__ chal,
               uint32_t n, uint32_t B, fe_t* __restrict__ num, fe_t* __restrict__ den, DevConsts C) {
     const uint32_t s = blockIdx.y, p = blockIdx.z, row = blockIdx.x * 256 + threadIdx.x;
-    if (row >= n) return;
+    // beta * delta^c of this proof's columns, once per CTA (one product per row and column less)
+    __shared__ uint4 bd_raw[CHUNK * 2];
+    fe_t* bd = reinterpret_cast<fe_t*>(bd_raw);
     const fe_t beta = ldv(chal + (size_t)p * 8 + 1), gamma = ldv(chal + (size_t)p * 8 + 2);
+    if (threadIdx.x < CHUNK && s * CHUNK + threadIdx.x < NPERM) stv(bd + threadIdx.x, Fr::mul(C.delta_pows[s * CHUNK + threadIdx.x], beta));
+    __syncthreads();
+    if (row >= n) return;
     const fe_t w = omega_pow(tw, n, row);
     fe_t nu = Fr::one(), de = Fr::one();
     for (int c = s * CHUNK; c < (int)(s + 1) * CHUNK && c < NPERM; c++) {
         fe_t v = c < NADV ? ldv(P + ((size_t)(SL_ADV + c) * B + p) * n + row) : Fr::zero();  // instance column: empty
         fe_t vg = Fr::add(v, gamma);
-        nu = Fr::mul(nu, Fr::add(Fr::mul(Fr::mul(C.delta_pows[c], w), beta), vg));
-        de = Fr::mul(de, Fr::add(Fr::mul(beta, ldv_nc(sigma_values + (size_t)c * n + row)), vg));
+        const fe_t fn = Fr::add(Fr::mul(ldv(bd + (c - s * CHUNK)), w), vg);
+        const fe_t fd = Fr::add(Fr::mul(beta, ldv_nc(sigma_values + (size_t)c * n + row)), vg);
+        nu = c == (int)(s * CHUNK) ? fn : Fr::mul(nu, fn);   // the first factor needs no product
+        de = c == (int)(s * CHUNK) ? fd : Fr::mul(de, fd);
     }
     const size_t o = ((size_t)s * B + p) * n + row;
     stv(num + o, nu);
