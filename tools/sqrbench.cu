@@ -1,6 +1,7 @@
 // Development tool: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o sqrbench sqrbench.cu
 // Device parity of the dedicated Montgomery squaring (field.cuh Field::sqr: 36 + 64 wide MADs) against mul(a, a) for
-// Fq and Fr, and the throughput of both.
+// Fq and Fr, the throughput of both, and the throughput of the fused sums of products (mul_add_mul: 192 wide MADs for two
+// products, dot4: 320 for four).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +23,16 @@ __global__ void k_chain(fe_t* out, const fe_t* in, int iters) {
     fe_t r = x[0];
     for (int j = 1; j < ILP; j++) r = F::add(r, x[j]);
     out[t] = r;
+}
+// OP 2: x = x*a + x*b (mul_add_mul), OP 3: x = x*a + x*b + x*a + x*b (dot4): dependent chains like k_chain
+template <class F, int OP>
+__global__ void k_fused(fe_t* out, const fe_t* in, int iters) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    fe_t x = in[t & 1023];
+    const fe_t a = in[(t + 7) & 1023], b = in[(t + 13) & 1023];
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) x = OP == 2 ? F::mul_add_mul(x, a, x, b) : F::dot4(x, a, x, b, x, a, x, b);
+    out[t] = x;
 }
 template <class F>
 __global__ void k_seed(fe_t* io, int n) {
@@ -68,6 +79,14 @@ template <class F> static void run(const char* name, int sms) {
         double ts2 = time_ms([&] { k_chain<F, 2, true><<<g, th>>>(o1, in, 512); });
         printf("%s warps/SM %2d  mul ILP1 %6.1f ILP2 %6.1f   sqr ILP1 %6.1f ILP2 %6.1f  G/s\n", name, cps * th / 32, m / tm1 / 1e6, 2 * m / tm2 / 1e6,
                m / ts1 / 1e6, 2 * m / ts2 / 1e6);
+    }
+    for (int cps : {4, 8}) {
+        const int g = sms * cps;
+        const double m = (double)g * th * 512;
+        double t2 = time_ms([&] { k_fused<F, 2><<<g, th>>>(o1, in, 512); });
+        double t4 = time_ms([&] { k_fused<F, 3><<<g, th>>>(o1, in, 512); });
+        printf("%s warps/SM %2d  mul_add_mul %6.1f G/s = %6.1f G products/s   dot4 %6.1f G/s = %6.1f G products/s\n", name, cps * th / 32, m / t2 / 1e6,
+               2 * m / t2 / 1e6, m / t4 / 1e6, 4 * m / t4 / 1e6);
     }
     cudaFree(in); cudaFree(o1); cudaFree(o2);
 }
