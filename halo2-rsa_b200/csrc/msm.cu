@@ -775,8 +775,11 @@ k_bucket_fixup(const uint32_t* __restrict__ offsets, uint32_t B, const xyzz_t* _
 //   level 3  CTA per vector over the nu = B / 256 level-2 outputs: W = sum_u u S2_u (suffix scan + tree), sums of A2, P1
 //   result = P1 + 32 (A2 + 8 W), one inversion to affine.
 static constexpr uint32_t BR_PER1 = 32, BR_PER2 = 8, BR_T3 = 128;
+#ifndef B2R_BR1_MINB
+#define B2R_BR1_MINB 3
+#endif
 
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, B2R_BR1_MINB)
 k_br_level1(const xyzz_t* __restrict__ buckets, uint32_t B, uint32_t nseg, xyzz_t* __restrict__ S1, xyzz_t* __restrict__ A1) {
     const uint32_t g = blockIdx.y, s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < nseg;  // no early return: the warp votes below need every lane
