@@ -534,6 +534,16 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         }
         if (log_c > log_cols) log_c = log_cols;
         if (p > 0 && log_c > log_s) log_c = log_s;
+        // CTA size: 128 threads on half the columns (up to 8 CTAs per SM instead of 4 x 256 threads).  Same registers, same
+        // shared memory per SM, same work per thread - but a barrier now waits for 4 warps instead of 8 and twice as many CTAs
+        // are in different phases (load / butterflies / store) at any time: 64 x 2^17 1.323 -> 1.254 ms, 64 x 2^19 5.644 ->
+        // 5.378 ms (tools/microbench.py; quarter-size CTAs: 1.325 / 5.346).  B2R_NTT_HALF = 0 / 1 / 2 is the tuning hook.
+        unsigned threads = 256;
+        {
+            const char* ov = getenv("B2R_NTT_HALF");
+            const uint32_t h = ov ? (uint32_t)atoi(ov) : 1u;
+            if (h >= 1 && h <= 2 && log_c >= h + 1) { threads = 256u >> h; log_c -= h; }
+        }
         A.log_c = log_c;
         size_t smem = ((size_t)sizeof(fe_t) << S[p]) << log_c;
         // passes behind the first: the CTA's columns share their twiddles (log_c <= log_s) and can stage them in shared memory
@@ -588,7 +598,7 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         if (!use_tma) {
             dim3 grid(1u << (log_cols - log_c), (unsigned)batch);
             { KTimer kt(ctx, "ntt_pass", (double)batch * n);
-            kern<<<grid, 256, smem, ctx->stream>>>(A); }
+            kern<<<grid, threads, smem, ctx->stream>>>(A); }
             B2R_LAUNCH_CHECK(ctx);
         }
         if (last && dst != out) {
