@@ -84,6 +84,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_rsa_prove_batch_ex": [vp, vp, vp, vp, vp, sz, vp, u64, u32, vp, vp],
         "b2r_pk_set_transcript_repr": [vp, vp],
         "b2r_field_selftest": [vp, u32, u32, vp, vp, vp, vp, vp, sz],
+        "b2r_sha256_batch": [vp, vp, vp, sz, vp, vp],
+        "b2r_sha256_batch_dev": [vp, vp, vp, sz, vp, vp],
+        "b2r_rsa_prove_msgs_batch": [vp, vp, vp, vp, vp, vp, sz, vp, u64, u32, vp, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the ABI symbol is missing: loud by design
@@ -302,6 +305,22 @@ class Context:
         self._ck(self.lib.b2r_rsa_keygen(self.h, prog.h, g.h, g_lagrange.h, C.byref(h)))
         return ProvingKey(self, h, prog)
 
+    # -- SHA-256 front end of RSASignatureVerifier (reference src/lib.rs:204-211), value level
+    @staticmethod
+    def _pack_msgs(msgs):
+        offs = np.zeros(len(msgs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+        buf = np.frombuffer(b"".join(bytes(m) for m in msgs) or b"\0", dtype=np.uint8).copy()
+        return buf, offs
+
+    def sha256_batch(self, msgs):
+        """-> (hash_limbs uint64[batch, 4], digests uint8[batch, 32]) computed on the device"""
+        buf, offs = self._pack_msgs(msgs)
+        limbs = np.zeros((len(msgs), 4), dtype=np.uint64)
+        dig = np.zeros((len(msgs), 32), dtype=np.uint8)
+        self._ck(self.lib.b2r_sha256_batch(self.h, _host_ptr(buf), _host_ptr(offs), len(msgs), _host_ptr(limbs), _host_ptr(dig)))
+        return limbs, dig
+
     # -- RSA witness (Circuit::synthesize of the pkcs1v15 circuit)
     def rsa_program(self, bits_len: int, k: int, e: int = 65537) -> "RsaProgram":
         e_le = np.frombuffer(e.to_bytes((e.bit_length() + 7) // 8, "little"), dtype=np.uint8).copy()
@@ -386,6 +405,30 @@ class ProvingKey:
         return proofs, status
 
     PROVE_INPUTS_ON_DEVICE, PROVE_SEED64 = 1, 2
+
+    def prove_msgs_batch(self, n_limbs, sig_limbs, msgs, seed, nonce: int = 0):
+        """RSASignatureVerifier::verify_pkcs1v15_signature from the message bytes on: SHA-256 on the device, then
+        create_proof -> (proofs, status, digests uint8[batch, 32]).  seed: int (test seed) or the 32-byte ChaCha20 key"""
+        n_limbs = np.ascontiguousarray(n_limbs, dtype=np.uint64)
+        sig_limbs = np.ascontiguousarray(sig_limbs, dtype=np.uint64)
+        batch = n_limbs.shape[0]
+        assert len(msgs) == batch
+        buf, offs = Context._pack_msgs(msgs)
+        flags = 0
+        if isinstance(seed, (bytes, bytearray)):
+            if len(seed) != 32:
+                raise ValueError("seed bytes must be the 32-byte ChaCha20 key")
+            key = bytes(seed)
+        else:
+            key = int(seed).to_bytes(8, "little") + bytes(24)
+            flags |= self.PROVE_SEED64
+        kb = (C.c_uint8 * 32).from_buffer_copy(key)
+        proofs = np.zeros((batch, self.proof_bytes), dtype=np.uint8)
+        status = np.zeros(batch, dtype=np.uint8)
+        dig = np.zeros((batch, 32), dtype=np.uint8)
+        self.ctx._ck(self.ctx.lib.b2r_rsa_prove_msgs_batch(self.ctx.h, self.h, _host_ptr(n_limbs), _host_ptr(sig_limbs), _host_ptr(buf), _host_ptr(offs),
+                                                          batch, C.cast(kb, C.c_void_p), nonce, flags, _host_ptr(proofs), _host_ptr(status), _host_ptr(dig)))
+        return proofs, status, dig
 
     def prove_batch_raw(self, n_ptr: int, s_ptr: int, h_ptr: int, batch: int, seed, proofs_ptr: int, status_ptr: int,
                         inputs_on_device: bool = False, nonce: int | None = None):

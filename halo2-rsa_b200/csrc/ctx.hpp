@@ -139,6 +139,11 @@ struct KTimer {
 // scratch arena slots
 enum { SC_NTT_PING = 0, SC_NTT_PONG = 1, SC_MSM_A = 2, SC_MSM_B = 3, SC_MSM_C = 4, SC_STAGE = 5, SC_WIT = 6, SC_MISC = 7 };
 
+// sha256.cu
+int32_t sha256_msgs_dev(b2r_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t batch, uint64_t* d_hash_limbs, uint32_t limb_stride,
+                        uint8_t* d_digests);
+int32_t sha256_check_offsets(b2r_ctx* ctx, const uint64_t* offsets, size_t batch);
+
 // ntt.cu
 int32_t ntt_get_twiddles(b2r_ctx* ctx, const fe_t& omega, uint32_t log_n, const fe_t** out);
 

@@ -50,6 +50,7 @@ struct NttPassArgs {
     uint32_t log_c;  // columns per CTA
     uint32_t pre;    // multiply input element i by pre3[i % 3]
     uint32_t post;   // multiply output element i by post3[i % 3]
+    uint32_t vec_fast;  // 0: grid (tiles, vectors); else 1-D grid, vector = blockIdx.x % vec_fast, tile = blockIdx.x / vec_fast
     fe_t pre3[3];
     fe_t post3[3];
 };
@@ -240,10 +241,12 @@ __global__ void __launch_bounds__(256, 4) k_ntt_pass(const NttPassArgs A) {
     const uint32_t T = blockDim.x, tid = threadIdx.x;
     const uint32_t log_c = A.log_c, cmask = (1u << log_c) - 1;
     const uint32_t log_cols = A.log_n - S;  // columns = n / R
-    const uint32_t c0 = blockIdx.x << log_c;
-    const fe_t* x = A.in_inner ? A.x + (uint64_t)(blockIdx.y / A.in_inner) * A.in_stride2 + (uint64_t)(blockIdx.y % A.in_inner) * A.in_stride
-                               : A.x + (uint64_t)blockIdx.y * A.in_stride;
-    fe_t* y = A.y + (uint64_t)blockIdx.y * A.out_stride;
+    // vec_fast: CTAs that are resident together work on the SAME column tile of different vectors, i.e. on the same twiddles
+    const uint32_t vec = A.vec_fast ? blockIdx.x % A.vec_fast : blockIdx.y;
+    const uint32_t c0 = (A.vec_fast ? blockIdx.x / A.vec_fast : blockIdx.x) << log_c;
+    const fe_t* x = A.in_inner ? A.x + (uint64_t)(vec / A.in_inner) * A.in_stride2 + (uint64_t)(vec % A.in_inner) * A.in_stride
+                               : A.x + (uint64_t)vec * A.in_stride;
+    fe_t* y = A.y + (uint64_t)vec * A.out_stride;
 
     // ---- load R rows x C columns (row r of column c lives at c + (n/R)*r)
     for (uint32_t idx = tid; idx < (R << log_c); idx += T) {
@@ -506,6 +509,7 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         A.log_n = log_n;
         A.log_s = log_s;
         A.pre = 0;
+        A.vec_fast = 0;
         A.post = 0;
         for (int j = 0; j < 3; j++) A.pre3[j] = A.post3[j] = Fr::one();
         if (p == 0 && mode == MODE_COSET_FWD) {
@@ -597,6 +601,15 @@ static int32_t ntt_run(b2r_ctx* ctx, const fe_t* in, uint64_t in_stride, uint32_
         }
         if (!use_tma) {
             dim3 grid(1u << (log_cols - log_c), (unsigned)batch);
+            A.vec_fast = 0;
+            {   // tuning hook: B2R_NTT_ORDER=1 walks the batch first (twiddles shared by the resident CTAs); =2 only in the first pass
+                const char* ov = getenv("B2R_NTT_ORDER");
+                const int o = ov ? atoi(ov) : 0;
+                if (batch > 1 && (o == 1 || (o == 2 && p == 0) || (o == 3 && p > 0)) && ((uint64_t)batch << (log_cols - log_c)) < (1ull << 31)) {
+                    A.vec_fast = (uint32_t)batch;
+                    grid = dim3((unsigned)(batch << (log_cols - log_c)), 1);
+                }
+            }
             { KTimer kt(ctx, "ntt_pass", (double)batch * n);
             kern<<<grid, threads, smem, ctx->stream>>>(A); }
             B2R_LAUNCH_CHECK(ctx);

@@ -1316,4 +1316,48 @@ int32_t b2r_rsa_prove_batch_ex(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n
     return prove_entry(ctx, pk, n_limbs, sig_limbs, hash_limbs, batch, bkey, (flags & B2R_PROVE_INPUTS_ON_DEVICE) != 0, proofs, status);
 } B2R_ABI_CATCH(ctx)
 
+// RSASignatureVerifier::verify_pkcs1v15_signature from the MESSAGE on (reference src/lib.rs:183-248): SHA-256 of every
+// message on the device (sha256.cu) -> the digest limbs of the sha_tail program's byte cells -> create_proof
+int32_t b2r_rsa_prove_msgs_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs, const uint8_t* msgs,
+                                 const uint64_t* msg_offsets, size_t batch, const uint8_t seed32[32], uint64_t nonce, uint32_t flags,
+                                 uint8_t* proofs, uint8_t* status, uint8_t* digests) try {
+    B2R_ENTER(ctx);
+    if (!pk || !n_limbs || !sig_limbs || !msg_offsets || !seed32 || !proofs || !status) return fail(ctx, B2R_ERR_INVALID, "rsa_prove_msgs: null pointer");
+    if (flags & ~(uint32_t)B2R_PROVE_SEED64) return fail(ctx, B2R_ERR_INVALID, "rsa_prove_msgs: unknown flag (inputs are host buffers)");
+    if (pk->prog->aux_words != 4) return fail(ctx, B2R_ERR_INVALID, "rsa_prove_msgs: the key's program does not take a 4-limb digest");
+    if (batch == 0) return 0;
+    if (batch > 0xffffffffull) return fail(ctx, B2R_ERR_INVALID, "rsa_prove_msgs: batch too large");
+    BlindKey bkey;
+    if (flags & B2R_PROVE_SEED64) {
+        uint64_t s64 = 0;
+        for (int i = 0; i < 8; i++) s64 |= (uint64_t)seed32[i] << (8 * i);
+        if (s64 == 0) return fail(ctx, B2R_ERR_INVALID, "rsa_prove_msgs: seed must be non-zero (blinding rows)");
+        bkey = blind_key_from_seed64(s64, nonce);
+    } else {
+        bkey = blind_key_from_bytes(seed32, nonce);
+    }
+    B2R_TRY(sha256_check_offsets(ctx, msg_offsets, batch));
+    const uint64_t base = msg_offsets[0], total = msg_offsets[batch] - base;
+    if (total && !msgs) return fail(ctx, B2R_ERR_INVALID, "rsa_prove_msgs: null message buffer");
+    const size_t nl = pk->prog->num_limbs;
+    const size_t in_bytes = (batch * (2 * nl + 4) * 8 + 255) & ~(size_t)255, off_bytes = ((batch + 1) * 8 + 255) & ~(size_t)255,
+                 dig_bytes = (batch * 32 + 255) & ~(size_t)255;
+    char* d = nullptr;
+    B2R_TRY(scratch_get(ctx, SC_MISC, in_bytes + off_bytes + dig_bytes + total + 256, (void**)&d));
+    uint64_t *d_n = (uint64_t*)d, *d_s = d_n + batch * nl, *d_h = d_s + batch * nl;
+    uint64_t* d_off = (uint64_t*)(d + in_bytes);
+    uint8_t* d_dig = (uint8_t*)(d + in_bytes + off_bytes);
+    uint8_t* d_msgs = (uint8_t*)(d + in_bytes + off_bytes + dig_bytes);
+    std::vector<uint64_t> rel(batch + 1);
+    for (size_t i = 0; i <= batch; i++) rel[i] = msg_offsets[i] - base;
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_n, n_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_s, sig_limbs, batch * nl * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_CUDA(ctx, cudaMemcpyAsync(d_off, rel.data(), (batch + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (total) B2R_CUDA(ctx, cudaMemcpyAsync(d_msgs, msgs + base, total, cudaMemcpyHostToDevice, ctx->stream));
+    B2R_TRY(sha256_msgs_dev(ctx, d_msgs, d_off, batch, d_h, 4, d_dig));
+    if (digests) B2R_CUDA(ctx, cudaMemcpyAsync(digests, d_dig, batch * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `rel` leaves scope below; the digests are complete for the caller
+    return prove_all(ctx, pk, d_n, d_s, d_h, batch, bkey, proofs, status);
+} B2R_ABI_CATCH(ctx)
+
 }  // extern "C"

@@ -260,6 +260,30 @@ int32_t b2r_rsa_prove_batch_ex(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n
                                const uint64_t* hash_limbs, size_t batch, const uint8_t seed32[32], uint64_t nonce,
                                uint32_t flags, uint8_t* proofs, uint8_t* status);
 
+/* ---- SHA-256 front end -----------------------------------------------------------
+ * RSASignatureVerifier::verify_pkcs1v15_signature (reference src/lib.rs:183-248) starts from the signed MESSAGE:
+ * step 1 hashes it (`sha256.finalize`, `decompose_digest_to_bytes`, `hashed_bytes.reverse()`, :204-211), step 2
+ * composes the digest bytes into four limbs and verifies (:218-245, built as b2r_rsa_program_build_sha_tail).
+ * These entry points are step 1 at the value level, on the GPU: SHA-256 (FIPS 180-4; the reference's bench and tests
+ * take the same digest from the `sha2` crate, benches/bench.rs:255-268) of `batch` messages, message i being
+ * msgs[offsets[i] .. offsets[i + 1]) (offsets: batch + 1 non-decreasing entries; empty messages allowed).
+ * hash_limbs: batch x 4 words, the digest read as a big-endian integer in little-endian 64-bit limbs - the third
+ * input array of b2r_rsa_witness_batch / b2r_rsa_prove_batch for the pkcs1v15 and sha_tail programs; digests:
+ * batch x 32 bytes in SHA order (the `hashed_bytes` the reference returns, :246-247).  Either output may be NULL.
+ * The constraint layout of the compression function belongs to halo2-dynamic-sha256 (unpinned external crate, not
+ * vendored) and is not reproduced: see DESIGN.md section 7. */
+int32_t b2r_sha256_batch(b2r_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t batch, uint64_t* hash_limbs,
+                         uint8_t* digests);
+int32_t b2r_sha256_batch_dev(b2r_ctx* ctx, const uint8_t* msgs_dev, const uint64_t* offsets_dev, size_t batch,
+                             uint64_t* hash_limbs_dev, uint8_t* digests_dev);
+/* message bytes -> proofs in one call for a key over a program that takes a 4-limb digest (b2r_rsa_program_build or
+ * b2r_rsa_program_build_sha_tail): HOST inputs, the messages are hashed on the device and never leave it; seed32 /
+ * nonce / flags as in b2r_rsa_prove_batch_ex (B2R_PROVE_SEED64 only); digests (batch x 32 bytes, may be NULL) returns
+ * the `hashed_bytes` of every instance. */
+int32_t b2r_rsa_prove_msgs_batch(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n_limbs, const uint64_t* sig_limbs,
+                                 const uint8_t* msgs, const uint64_t* msg_offsets, size_t batch, const uint8_t seed32[32],
+                                 uint64_t nonce, uint32_t flags, uint8_t* proofs, uint8_t* status, uint8_t* digests);
+
 #ifdef __cplusplus
 }
 #endif

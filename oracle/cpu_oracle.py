@@ -42,6 +42,23 @@ def ncores():
     return os.cpu_count() or 1
 
 
+def sha256(msg: bytes) -> bytes:
+    """oracle/sha256.c: FIPS 180-4 (the digest the reference takes from the `sha2` crate, benches/bench.rs:255-268)"""
+    m = np.frombuffer(bytes(msg) or b"\0", dtype=np.uint8).copy()
+    out = np.zeros(32, dtype=np.uint8)
+    lib().orc_sha256(_p(m), C.c_uint64(len(msg)), _p(out))
+    return out.tobytes()
+
+
+def sha256_hashed_limbs(msg: bytes):
+    """-> (digest bytes least significant first = the byte cells of src/lib.rs:210-211, the four 64-bit limbs of :222-236)"""
+    m = np.frombuffer(bytes(msg) or b"\0", dtype=np.uint8).copy()
+    d = np.zeros(32, dtype=np.uint8)
+    l = np.zeros(4, dtype=np.uint64)
+    lib().orc_sha256_hashed_limbs(_p(m), C.c_uint64(len(msg)), _p(d), _p(l))
+    return d, l
+
+
 def best_fft(a: np.ndarray, omega: np.ndarray, log_n: int, threads: int = 0) -> np.ndarray:
     a = np.ascontiguousarray(a, dtype=np.uint64).copy()
     omega = np.ascontiguousarray(omega, dtype=np.uint64)
