@@ -409,6 +409,11 @@ def main():
                                "frac": ntt_ach / peak, "traffic": tr, "ms_per_step": nms / args.steps, "launches_per_step": ncnt / args.steps,
                                "share_of_step": nms / ms, "algorithmic_bytes_per_step": ntt_alg / args.steps}
                 roof["ntt"].update(extra_n)
+                if tr is not None:
+                    # the capture covers whole steps' launches: per-step DRAM traffic = mean per launch x launches per step; it is
+                    # the algorithmic 2 * n * 32 B per transform times the number of passes (2 at 2^17, 3 at 2^19): no re-reads
+                    roof["ntt"]["traffic_per_step"] = tr * ncnt / args.steps
+                    roof["ntt"]["traffic_over_algorithmic"] = tr * ncnt / ntt_alg
         line = {
             "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
