@@ -276,9 +276,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # ONE JSON line on stdout: libraries write banners to file descriptor 1 (NCCL prints "NCCL version ..." there whenever
+    # NCCL_DEBUG is VERSION / WARN / INFO in the environment), so fd 1 is pointed at stderr for the whole run and the
+    # result line goes to the saved descriptor
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keeps NCCL's "NCCL version ..." banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     side = torch.cuda.Stream(device=dev)
@@ -396,7 +401,9 @@ def main():
                                 "how": "bucket entries counted by the library (zero digits and, for the grand-product columns, rows where the "
                                        "column does not change are skipped) / kernel time; peak = 148 SMs x 32 IMAD.WIDE lanes/clk / "
                                        "(6 products x 128 + 2 squarings x 100 + 1 fused product pair x 192 = 1160 IMAD.WIDE per mixed addition) at 1965 MHz"}
-            roof["traffic"], extra_t = recorded_traffic("k_accum_entries", MSM_SOURCES)
+            captured_cfg = args.workload == "rsa2048" and batch == 64   # what profiles/traffic.json was captured on
+            roof["traffic"], extra_t = recorded_traffic("k_accum_entries", MSM_SOURCES) if captured_cfg else \
+                (None, {"traffic_note": "profiles/traffic.json is a capture of the rsa2048 / batch 64 step"})
             roof.update(extra_t)
             if "ntt_pass" in prof:
                 # second entry: the NTT passes, the kernel closest to being HBM relevant.  Algorithmic bytes per transform
@@ -404,7 +411,8 @@ def main():
                 nms, ncnt = prof["ntt_pass"]
                 ntt_alg = args.steps * batch * (INTT_PER_PROOF * 2 * n * 32 + (COSET_PER_PROOF + 1) * 2 * (n << (EXT_K - K)) * 32)
                 ntt_ach = ntt_alg / (nms / 1e3) / 1e9
-                tr, extra_n = recorded_traffic("k_ntt_pass", NTT_SOURCES)
+                tr, extra_n = recorded_traffic("k_ntt_pass", NTT_SOURCES) if captured_cfg else \
+                    (None, {"traffic_note": "profiles/traffic.json is a capture of the rsa2048 / batch 64 step"})
                 roof["ntt"] = {"bound": "hbm", "kernel": "k_ntt_pass (all passes of the 45 transforms per proof)", "achieved": ntt_ach, "peak": peak, "unit": "GB/s",
                                "frac": ntt_ach / peak, "traffic": tr, "ms_per_step": nms / args.steps, "launches_per_step": ncnt / args.steps,
                                "share_of_step": nms / ms, "algorithmic_bytes_per_step": ntt_alg / args.steps}
@@ -435,7 +443,8 @@ def main():
             t = cpu_port_step(sample, threads)
             line["cpu_baseline"] = {"value": sample / t, "unit": "proofs/s", "cores": threads, "kind": "port",
                                     "sample": f"{sample} complete proofs of the same workload, one after the other: synthesize on 1 thread + the whole create_proof (oracle/plonk_prover.c) on {threads} threads ({t:.1f} s)"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
