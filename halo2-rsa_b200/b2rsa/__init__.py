@@ -84,6 +84,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "b2r_rsa_prove_batch_ex": [vp, vp, vp, vp, vp, sz, vp, u64, u32, vp, vp],
         "b2r_pk_set_transcript_repr": [vp, vp],
         "b2r_field_selftest": [vp, u32, u32, vp, vp, vp, vp, vp, sz],
+        "b2r_last_commitments": [vp, vp, sz, u32, C.POINTER(sz), C.POINTER(u32)],
         "b2r_sha256_batch": [vp, vp, vp, sz, vp, vp],
         "b2r_sha256_batch_dev": [vp, vp, vp, sz, vp, vp],
         "b2r_rsa_prove_msgs_batch": [vp, vp, vp, vp, vp, vp, sz, vp, u64, u32, vp, vp, vp],
@@ -304,6 +305,23 @@ class Context:
         h = C.c_void_p()
         self._ck(self.lib.b2r_rsa_keygen(self.h, prog.h, g.h, g_lagrange.h, C.byref(h)))
         return ProvingKey(self, h, prog)
+
+    # -- device-resident commitment block of the last prove call (the multi-GPU all-gather payload)
+    def last_commitments_info(self):
+        b, per = C.c_size_t(), C.c_uint32()
+        self._ck(self.lib.b2r_last_commitments(self.h, None, 0, 0, C.byref(b), C.byref(per)))
+        return b.value, per.value
+
+    def last_commitments(self) -> np.ndarray:
+        """-> uint64[batch, 31, 8] (host copy)"""
+        b, per = self.last_commitments_info()
+        out = np.zeros((b, per, 8), dtype=np.uint64)
+        self._ck(self.lib.b2r_last_commitments(self.h, _host_ptr(out), b * per, 0, None, None))
+        return out
+
+    def last_commitments_dev(self, dst_ptr: int, capacity_points: int):
+        """device-to-device copy into a caller-owned buffer (e.g. a torch tensor's data_ptr) on the context's stream"""
+        self._ck(self.lib.b2r_last_commitments(self.h, C.c_void_p(dst_ptr), capacity_points, 1, None, None))
 
     # -- SHA-256 front end of RSASignatureVerifier (reference src/lib.rs:204-211), value level
     @staticmethod

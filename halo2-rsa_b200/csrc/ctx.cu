@@ -89,6 +89,7 @@ int32_t b2r_ctx_destroy(b2r_ctx* ctx) {
     for (auto& r : ctx->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->commit_log) cudaFree(ctx->commit_log);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

@@ -56,6 +56,11 @@ struct b2r_ctx {
     std::vector<cudaEvent_t> prof_pool;
     void* pinned = nullptr;  // small pinned staging block
     size_t pinned_cap = 0;
+    // commitments of the last prove call, device resident: [batch][31] affine points in transcript order
+    // (b2r_last_commitments; the block a multi-GPU host all-gathers)
+    void* commit_log = nullptr;
+    size_t commit_log_cap = 0;    // proofs
+    size_t commit_log_batch = 0;  // proofs of the last completed call (0 = none)
 };
 
 namespace b2r {

@@ -425,6 +425,20 @@ __global__ void __launch_bounds__(256) k_run_diff(const fe_t* __restrict__ Z /* 
     stv(D + (size_t)z * n + row, row ? Fr::sub(cur, ldv(a + row - 1)) : cur);
 }
 
+// ---- device-resident commitment block ---------------------------------------------------------------------------
+// log[(p_base + p) * NCOMMIT + off + j] = the j-th commitment of this phase for proof p, read from the phase's MSM output:
+// mode 0: src[j * B + p] (column-major phases), 1: src[p * J + j] (per-proof phases), 2: the permuted-lookup phase, whose MSM
+// output holds all A' then all S' while the transcript interleaves them (A'_0, S'_0, A'_1, ...)
+static constexpr uint32_t NCOMMIT = NADV + 2 * NLOOK + (NZ + 1) + QD + NPOINTS;
+__global__ void __launch_bounds__(256) k_log_commitments(const affine_t* __restrict__ src, affine_t* __restrict__ log, uint32_t B, uint32_t J, uint32_t off,
+                                                        uint32_t p_base, uint32_t mode) {
+    const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= B * J) return;
+    const uint32_t p = t / J, j = t % J;
+    const uint32_t si = mode == 0 ? j * B + p : mode == 1 ? p * J + j : ((j & 1u) * (J / 2) + (j >> 1)) * B + p;
+    log[(size_t)(p_base + p) * NCOMMIT + off + j] = src[si];
+}
+
 // ---- phase 4: quotient on the extended coset --------------------------------------------------------------------
 struct QuotArgs {
     const fe_t* E;        // [NTRANS][QB][ext_n]
@@ -1053,6 +1067,13 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
         B2R_CUDA(ctx, cudaStreamSynchronize(st));
         return 0;
     };
+    // every phase also files its commitments in the device-resident block (no host round trip: a copy kernel on the stream)
+    auto log_points = [&](uint32_t J, uint32_t off, uint32_t mode) -> int32_t {
+        if (!ctx->commit_log) return 0;
+        k_log_commitments<<<(B * J + 255) / 256, 256, 0, st>>>(S.cm, (affine_t*)ctx->commit_log, B, J, off, p_base, mode);
+        B2R_LAUNCH_CHECK(ctx);
+        return 0;
+    };
     auto push_chal = [&]() -> int32_t {
         B2R_CUDA(ctx, cudaMemcpyAsync(S.chal, chal.data(), chal.size() * 32, cudaMemcpyHostToDevice, st));
         return 0;
@@ -1066,6 +1087,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     B2R_TRY(witness_run(ctx, pk->prog, d_n, d_s, d_h, B, seed, (b2r_fr*)S.P, S.valid, p_base, /*p_stride=*/n, /*col_stride=*/(size_t)B * n));
     B2R_TRY(msm_batch_dev(ctx, pk->gl_c13, S.P + (size_t)SL_ADV * B * n, (size_t)NADV * B, n, S.cm, false));
     B2R_CUDA(ctx, cudaMemcpyAsync(valid.data(), S.valid, B, cudaMemcpyDeviceToHost, st));
+    B2R_TRY(log_points(NADV, 0, 0));
     B2R_TRY(fetch_points((size_t)NADV * B));
     parallel_for_proofs(B, [&](uint32_t p) {
         tr[p].common_scalar(pk->transcript_repr);
@@ -1102,6 +1124,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
         B2R_TRY(msm_batch_dev(ctx, pk->gl_c10, SS, (size_t)NLOOK * B, n, S.cm + (size_t)NLOOK * B, false));
     }
     B2R_CUDA(ctx, cudaMemcpyAsync(err.data(), S.err, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    B2R_TRY(log_points(2 * NLOOK, NADV, 2));
     B2R_TRY(fetch_points((size_t)2 * NLOOK * B));
     parallel_for_proofs(B, [&](uint32_t p) {
         for (int j = 0; j < 2 * NLOOK; j++) {   // halo2 writes A'_l, S'_l per lookup
@@ -1138,6 +1161,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     B2R_LAUNCH_CHECK(ctx);
     B2R_TRY(msm_batch_dev(ctx, pk->gl_sfx, S.num, (size_t)NZ * B, n, S.cm, true));   // non-zero differences of a grand product: uniform
     B2R_TRY(msm_batch_dev(ctx, pk->g, S.P + (size_t)SL_RAND * B * n, B, n, S.cm + (size_t)NZ * B, true));
+    B2R_TRY(log_points(NZ + 1, NADV + 2 * NLOOK, 0));
     B2R_TRY(fetch_points((size_t)(NZ + 1) * B));
     parallel_for_proofs(B, [&](uint32_t p) {
         for (int j = 0; j < NZ + 1; j++) tr[p].write_point(cm[(size_t)j * B + p].x, cm[(size_t)j * B + p].y);
@@ -1170,6 +1194,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
                                         cudaMemcpyDeviceToDevice, st));
     }
     B2R_TRY(msm_batch_dev(ctx, pk->g, S.hbuf, (size_t)QD * B, n, S.cm, true));
+    B2R_TRY(log_points(QD, NADV + 2 * NLOOK + NZ + 1, 1));
     B2R_TRY(fetch_points((size_t)QD * B));
     std::vector<fe_t> points((size_t)B * NPOINTS), scal((size_t)B * NPOINTS * MAXTERMS, Fr::zero()), xn(B);
     {
@@ -1231,6 +1256,7 @@ static int32_t prove_group(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, 
     k_kate<<<dim3(NPOINTS, B), 256, 0, st>>>(S.lc, S.points, n, S.wq); }
     B2R_LAUNCH_CHECK(ctx);
     B2R_TRY(msm_batch_dev(ctx, pk->g, S.wq, (size_t)NPOINTS * B, n, S.cm, true));
+    B2R_TRY(log_points(NPOINTS, NADV + 2 * NLOOK + NZ + 1 + QD, 1));
     B2R_TRY(fetch_points((size_t)NPOINTS * B));
     for (uint32_t p = 0; p < B; p++) {
         for (int g = 0; g < NPOINTS; g++) tr[p].write_point(cm[(size_t)p * NPOINTS + g].x, cm[(size_t)p * NPOINTS + g].y);
@@ -1258,11 +1284,24 @@ static int32_t prove_all(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* d_n, co
     const size_t per_proof = ((size_t)NSLOT + QD + 3 * NZ + 2 * NPOINTS) * pk->n * 32 + 4096;
     size_t G = std::max<size_t>(1, std::min<size_t>(64, ((size_t)48 << 30) / per_proof));
     if (const char* ov = getenv("B2R_PROVE_GROUP")) G = std::max<size_t>(1, std::min<size_t>(G, (size_t)atoi(ov)));  // tests: force several groups
+    // device-resident commitment block of this call (b2r_last_commitments)
+    ctx->commit_log_batch = 0;
+    if (ctx->commit_log_cap < batch) {
+        if (ctx->commit_log) {
+            B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            B2R_CUDA(ctx, cudaFree(ctx->commit_log));
+            ctx->commit_log = nullptr;
+            ctx->commit_log_cap = 0;
+        }
+        B2R_CUDA(ctx, cudaMalloc(&ctx->commit_log, batch * NCOMMIT * sizeof(affine_t)));
+        ctx->commit_log_cap = batch;
+    }
     for (size_t p0 = 0; p0 < batch; p0 += G) {
         const uint32_t g = (uint32_t)std::min(G, batch - p0);
         B2R_TRY(prove_group(ctx, pk, d_n + p0 * nl, d_s + p0 * nl, d_h + p0 * pk->prog->aux_words, g, bkey, (uint32_t)p0, proofs + p0 * proof_bytes, status + p0,
                             (size_t)proof_bytes));
     }
+    ctx->commit_log_batch = batch;
     return 0;
 }
 
@@ -1314,6 +1353,19 @@ int32_t b2r_rsa_prove_batch_ex(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n
         bkey = blind_key_from_bytes(seed32, nonce);
     }
     return prove_entry(ctx, pk, n_limbs, sig_limbs, hash_limbs, batch, bkey, (flags & B2R_PROVE_INPUTS_ON_DEVICE) != 0, proofs, status);
+} B2R_ABI_CATCH(ctx)
+
+int32_t b2r_last_commitments(b2r_ctx* ctx, b2r_g1_affine* dst, size_t capacity_points, uint32_t dst_on_device, size_t* batch, uint32_t* per_proof) try {
+    B2R_ENTER(ctx);
+    if (batch) *batch = ctx->commit_log_batch;
+    if (per_proof) *per_proof = NCOMMIT;
+    if (!dst) return 0;   // query only
+    const size_t pts = ctx->commit_log_batch * NCOMMIT;
+    if (pts == 0) return fail(ctx, B2R_ERR_INVALID, "last_commitments: no completed prove call on this context");
+    if (capacity_points < pts) return fail(ctx, B2R_ERR_INVALID, "last_commitments: destination too small");
+    B2R_CUDA(ctx, cudaMemcpyAsync(dst, ctx->commit_log, pts * sizeof(affine_t), dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dst_on_device) B2R_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
 } B2R_ABI_CATCH(ctx)
 
 // RSASignatureVerifier::verify_pkcs1v15_signature from the MESSAGE on (reference src/lib.rs:183-248): SHA-256 of every

@@ -260,6 +260,18 @@ int32_t b2r_rsa_prove_batch_ex(b2r_ctx* ctx, const b2r_pk* pk, const uint64_t* n
                                const uint64_t* hash_limbs, size_t batch, const uint8_t seed32[32], uint64_t nonce,
                                uint32_t flags, uint8_t* proofs, uint8_t* status);
 
+/* The commitments of the last completed b2r_rsa_prove_batch* / b2r_rsa_prove_msgs_batch call on this context, DEVICE
+ * RESIDENT: batch x per_proof (= 31) affine points (Montgomery coordinates, identity (0, 0)) in the order the transcript
+ * absorbs them and the proof stream carries them compressed - 5 advice, 10 permuted lookup columns (A'_0, S'_0, A'_1, ..),
+ * 2 permutation + 5 lookup grand products, the random polynomial, 4 quotient pieces, 4 GWC witnesses.  This is the block
+ * a multi-GPU host all-gathers over NCCL without a host round trip (reference benches/bench.rs:319-331
+ * produces one proof per instance, the commitments are its first 27 and last 4 group elements).
+ * dst: capacity_points affine points, a DEVICE pointer if dst_on_device != 0 (device-to-device copy on the context's
+ * stream, not synchronised) else a HOST pointer; dst == NULL only queries batch / per_proof.  The block is overwritten by
+ * the next prove call. */
+int32_t b2r_last_commitments(b2r_ctx* ctx, b2r_g1_affine* dst, size_t capacity_points, uint32_t dst_on_device, size_t* batch,
+                             uint32_t* per_proof);
+
 /* ---- SHA-256 front end -----------------------------------------------------------
  * RSASignatureVerifier::verify_pkcs1v15_signature (reference src/lib.rs:183-248) starts from the signed MESSAGE:
  * step 1 hashes it (`sha256.finalize`, `decompose_digest_to_bytes`, `hashed_bytes.reverse()`, :204-211), step 2

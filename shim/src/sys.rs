@@ -72,6 +72,9 @@ extern "C" {
                                batch: usize, seed: u64, proofs: *mut u8, status: *mut u8) -> i32;
     pub fn b2r_rsa_prove_batch_ex(ctx: *mut b2r_ctx, pk: *const b2r_pk, n_limbs: *const u64, sig_limbs: *const u64, hash_limbs: *const u64,
                                   batch: usize, seed32: *const u8, nonce: u64, flags: u32, proofs: *mut u8, status: *mut u8) -> i32;
+    // device-resident commitments of the last prove call: batch x 31 affine points in transcript order (the all-gather payload)
+    pub fn b2r_last_commitments(ctx: *mut b2r_ctx, dst: *mut G1Affine, capacity_points: usize, dst_on_device: u32, batch: *mut usize,
+                                per_proof: *mut u32) -> i32;
     // ---- RSASignatureVerifier::verify_pkcs1v15_signature from the message bytes on (src/lib.rs:183-248): SHA-256 on the device
     pub fn b2r_sha256_batch(ctx: *mut b2r_ctx, msgs: *const u8, offsets: *const u64, batch: usize, hash_limbs: *mut u64, digests: *mut u8) -> i32;
     pub fn b2r_sha256_batch_dev(ctx: *mut b2r_ctx, msgs_dev: *const u8, offsets_dev: *const u64, batch: usize, hash_limbs_dev: *mut u64,

@@ -321,3 +321,30 @@ def test_empty_batches_and_argument_errors(ctx, small):
     assert lib.b2r_rsa_prove_batch_ex(h, pk.h, p(nl), p(sl), p(hl), 1, C.cast(zero, C.c_void_p), 1, 0, p(proofs), p(status)) == 0
     assert status[0] == 1 and PL.verify_proof(opk, srs.s, proofs.tobytes())
     g.free(); gl.free()
+
+
+def test_device_resident_commitment_block(ctx, small, monkeypatch):
+    """b2r_last_commitments: the 31 commitments per proof that stay on the device for the multi-GPU all-gather
+     are exactly the group elements of the proof stream - compressed, they equal the proof's first
+    27 points and its last 4 - for a batch that crosses a proof group, and a device-to-device copy returns the
+    same block as the host copy"""
+    import torch
+    bits, k, pk, srs, opk = small
+    monkeypatch.setenv("B2R_PROVE_GROUP", "2")          # three proofs in groups of 2: the block spans proof groups
+    nl, sl, hl = RF.batch(bits, 3, start=4)
+    proofs, status = pk.prove_batch(nl, sl, hl, seed=77)
+    assert status.tolist() == [1, 1, 1]
+    assert ctx.last_commitments_info() == (3, 31)
+    cm = ctx.last_commitments()
+    for p in range(3):
+        pts = np_to_g1(cm[p].reshape(-1, 8))
+        raw = bytes(proofs[p])
+        want = [raw[32 * i:32 * i + 32] for i in range(27)] + [raw[2848 - 128 + 32 * i:2848 - 96 + 32 * i] for i in range(4)]
+        assert [PL.compress_point(P) for P in pts] == want, f"proof {p}"
+    d = torch.zeros(3 * 31 * 8, dtype=torch.int64, device="cuda:0")
+    ctx.last_commitments_dev(d.data_ptr(), 3 * 31)
+    ctx.sync()
+    assert np.array_equal(d.cpu().numpy().view(np.uint64).reshape(3, 31, 8), cm)
+    import b2rsa
+    with pytest.raises(b2rsa.B2RError):
+        ctx.last_commitments_dev(d.data_ptr(), 3 * 31 - 1)   # destination too small
