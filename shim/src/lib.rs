@@ -171,6 +171,34 @@ impl<'a> RsaProver<'a> {
         })?;
         Ok((proofs, status))
     }
+    /// `RSASignatureVerifier::verify_pkcs1v15_signature` from the message bytes on (src/lib.rs:183-248): SHA-256 of every
+    /// message on the device, then `create_proof`.  -> (proofs, status, digests: batch x 32 bytes = `hashed_bytes`)
+    pub fn prove_msgs(&mut self, n_limbs: &[u64], sig_limbs: &[u64], msgs: &[&[u8]], seed: &[u8; 32]) -> Result<(Vec<u8>, Vec<u8>, Vec<u8>)> {
+        let nl = (self.bits_len / 64) as usize;
+        let batch = msgs.len();
+        assert!(n_limbs.len() == batch * nl && sig_limbs.len() == batch * nl);
+        let (mut offs, mut buf) = (vec![0u64], Vec::<u8>::new());
+        for m in msgs { buf.extend_from_slice(m); offs.push(buf.len() as u64); }
+        let mut proofs = vec![0u8; batch * self.proof_bytes];
+        let mut status = vec![0u8; batch];
+        let mut digests = vec![0u8; batch * 32];
+        self.nonce += 1;
+        self.gpu.check(unsafe {
+            sys::b2r_rsa_prove_msgs_batch(self.gpu.raw(), self.pk, n_limbs.as_ptr(), sig_limbs.as_ptr(), buf.as_ptr(), offs.as_ptr(), batch,
+                                          seed.as_ptr(), self.nonce, 0, proofs.as_mut_ptr(), status.as_mut_ptr(), digests.as_mut_ptr())
+        })?;
+        Ok((proofs, status, digests))
+    }
+    /// The commitments of the last `prove_*` call (batch x 31 affine points in transcript order), copied from their
+    /// device-resident block; a multi-GPU host passes a device pointer and `dst_on_device = 1` instead and hands that
+    /// buffer to `ncclAllGather`.
+    pub fn last_commitments(&self) -> Result<Vec<G1Affine>> {
+        let (mut batch, mut per) = (0usize, 0u32);
+        self.gpu.check(unsafe { sys::b2r_last_commitments(self.gpu.raw(), ptr::null_mut(), 0, 0, &mut batch, &mut per) })?;
+        let mut out = vec![G1Affine::default(); batch * per as usize];
+        self.gpu.check(unsafe { sys::b2r_last_commitments(self.gpu.raw(), out.as_mut_ptr(), out.len(), 0, ptr::null_mut(), ptr::null_mut()) })?;
+        Ok(out)
+    }
 }
 impl<'a> Drop for RsaProver<'a> {
     fn drop(&mut self) {
