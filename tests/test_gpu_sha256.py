@@ -49,8 +49,10 @@ def test_device_sha256_edge_cases(ctx):
     assert rc == b2rsa.ERR_INVALID
 
 
-def _signed(bits, count, tamper=()):
-    """count (n, sig, msg) triples; for i in `tamper` the message that is hashed differs from the one that was signed"""
+def _signed(bits, count, tamper=(), wrong_key=()):
+    """count (n, sig, msg) triples; for i in `tamper` the message that is hashed differs from the one that was signed,
+    for i in `wrong_key` the public key is another key's modulus (one above the signature, so that the reference's
+    assert_in_field passes and the verdict is a clean is_valid = 0) - the negative twins of src/lib.rs:541 and :626"""
     nl = bits // 64
     ks = RF.keys(bits)
     ns, ss, msgs = [], [], []
@@ -58,6 +60,8 @@ def _signed(bits, count, tamper=()):
         n, d = ks[i % len(ks)]
         msg = b"RSASignatureVerifier message %d " % i + bytes(range(i * 7 % 50))
         sig = pow(RF.emsa_pkcs1_v15(hashlib.sha256(msg).digest(), bits), d, n)
+        if i in wrong_key:
+            n = next(m for m, _ in ks if m != n and m > sig)
         ns.append(RF.limbs64(n, nl)); ss.append(RF.limbs64(sig, nl))
         msgs.append(msg + b"?" if i in tamper else msg)
     return np.stack(ns), np.stack(ss), msgs
@@ -69,12 +73,12 @@ def test_verifier_from_message_bytes_witness_and_proofs(ctx):
     are the `hashed_bytes` of src/lib.rs:246-247, and every proof is accepted by the oracle verifier (the verifier
     circuit returns the bit instead of asserting it, so the tampered instance still has a satisfying witness)"""
     bits, k = 1024, 15
-    nls, sls, msgs = _signed(bits, 3, tamper=(2,))
+    nls, sls, msgs = _signed(bits, 4, tamper=(2,), wrong_key=(3,))
     prog = ctx.rsa_program_sha_tail(bits, k)
     limbs, dig = ctx.sha256_batch(msgs)
     adv, valid = prog.witness_batch(nls, sls, limbs)
-    assert valid.tolist() == [1, 1, 0]
-    for i in range(3):
+    assert valid.tolist() == [1, 1, 0, 0]
+    for i in range(4):
         _, l = CO.sha256_hashed_limbs(msgs[i])
         t = CO.RsaTable(bits, k)
         assert t.synthesize_digest(nls[i], sls[i], l) == int(valid[i])
@@ -84,16 +88,16 @@ def test_verifier_from_message_bytes_witness_and_proofs(ctx):
     g, gl = ctx.srs_setup(k, fr_to_np([O.srs_secret(k)])[0])
     pk = ctx.rsa_keygen(prog, g, gl)
     proofs, status, digests = pk.prove_msgs_batch(nls, sls, msgs, seed=0x5A, nonce=3)
-    assert status.tolist() == [1, 1, 0]
-    for i in range(3):
+    assert status.tolist() == [1, 1, 0, 0]
+    for i in range(4):
         assert bytes(digests[i]) == hashlib.sha256(msgs[i]).digest()
     f, s_, t_ = pk.export_vk()
     vk = PL.vk_from_commitments(k, np_to_g1(f), np_to_g1(s_), np_to_fr(t_.reshape(1, 4))[0])
-    for i in range(3):
+    for i in range(4):
         assert PL.verify_proof(vk, O.srs_secret(k), bytes(proofs[i])), f"proof {i}"
     # the same proofs as from pre-hashed limbs with the same key / nonce: the front end changes nothing downstream
     proofs2, status2 = pk.prove_batch(nls, sls, limbs, seed=0x5A, nonce=3)
-    assert status2.tolist() == [1, 1, 0] and np.array_equal(proofs, proofs2)
+    assert status2.tolist() == [1, 1, 0, 0] and np.array_equal(proofs, proofs2)
     pk.free(); g.free(); gl.free(); prog.free()
 
 
