@@ -55,3 +55,24 @@ def test_message_level_verifier_on_the_oracle_table():
         assert t.synthesize_digest(RF.limbs64(n, nl), RF.limbs64(sig, nl), limbs) == want
         assert t.check()[0] == 0
         t.free()
+
+
+def test_device_sha256_source_host_build_matches_hashlib(tmp_path):
+    """the DEVICE implementation (csrc/sha256.cuh, what k_sha256_msgs runs) compiled for the host by g++ - like the host
+    build of field.cuh - against hashlib for every padding boundary, and its limbs against the oracle's"""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "sha_host")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(here, "host", "sha256_host_test.cpp")])
+    rnd = random.Random(11)
+    msgs = [bytes(rnd.getrandbits(8) for _ in range(n)) for n in list(range(0, 200)) + [247, 248, 255, 256, 1000, 4097]]
+    msgs += [m for m, _ in KATS[:3]]
+    inp = "\n".join(m.hex() if m else "-" for m in msgs) + "\n"
+    out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.splitlines()
+    assert len(out) == len(msgs)
+    for m, line in zip(msgs, out):
+        f = line.split()
+        assert f[0] == hashlib.sha256(m).hexdigest(), len(m)
+        _, limbs = CO.sha256_hashed_limbs(m)
+        assert [int(x, 16) for x in f[1:5]] == [int(v) for v in limbs]
